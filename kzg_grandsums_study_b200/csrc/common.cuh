@@ -1,0 +1,118 @@
+// Internal structures shared by the translation units of libkzgb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/kzgb200.h"
+#include "ec.cuh"
+
+struct kzg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    uint64_t launches = 0;
+    uint32_t msm_window = 0;  // 0 = auto
+    // twiddle tables (device): W = w_{2^26}; lo[i] = W^i, hi[j] = W^(j * 8192); [0] forward, [1] inverse
+    kzg::Fr* tw_lo[2] = {nullptr, nullptr};
+    kzg::Fr* tw_hi[2] = {nullptr, nullptr};
+    bool ntt_attr_set = false;
+    // persistent scratch (grown on demand)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // pinned host staging for small results
+    uint8_t* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    // small device slot for O(1)-sized results (commitment, evaluation values, status words)
+    uint8_t* dev_small = nullptr;
+    size_t dev_small_bytes = 0;
+};
+
+struct kzg_buf {
+    kzg::Fr* d = nullptr;
+    uint64_t n = 0;
+};
+
+struct kzg_srs {
+    kzg::G1Affine* d = nullptr;
+    uint64_t n = 0;
+    uint32_t power = 0;
+};
+
+namespace kzg {
+
+// twiddle tables: every power of W = w_{2^NTT_MAX_LOG} is hi[e >> TW_BITS] * lo[e & (TW_SIZE - 1)]
+constexpr uint32_t TW_BITS = 13;
+constexpr uint32_t TW_SIZE = 1u << TW_BITS;
+constexpr uint32_t NTT_MAX_LOG = 2 * TW_BITS;  // 26
+
+int set_err(kzg_ctx* ctx, int code, const std::string& msg);
+
+#define KZG_CUDA(ctx, expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return kzg::set_err(ctx, KZG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define KZG_TRY(expr)              \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != KZG_OK) return _r; \
+    } while (0)
+
+// launch bookkeeping: every kernel launch in the library goes through KZG_LAUNCH so that
+// kzg_ctx_launch_count() is an exact count.
+#define KZG_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);        \
+        (ctx)->launches++;                                                      \
+    } while (0)
+
+#define KZG_CHECK_LAUNCH(ctx) KZG_CUDA(ctx, cudaGetLastError())
+
+int ctx_scratch(kzg_ctx* ctx, size_t bytes, void** out);
+int buf_new(kzg_ctx* ctx, uint64_t n, bool zero, kzg_buf** out);
+
+// ---- internal device-level entry points (defined across the .cu files) ----
+// ntt.cu
+int ntt_run(kzg_ctx* ctx, const Fr* in, uint64_t n_in, Fr* out, uint32_t log_n, bool inverse);
+int ntt_init_tables(kzg_ctx* ctx);
+// msm.cu
+struct MsmScalarSrc {
+    const Fr* scalars;  // device
+    bool montgomery;    // true: convert from Montgomery on the fly (commit of a polynomial)
+};
+int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev);
+int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t count, uint8_t out[64]);
+// frops.cu
+int fr_convert(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n, bool to_mont);
+int fr_batch_inverse(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n);
+int poly_degree(kzg_ctx* ctx, const Fr* a, uint64_t n, uint64_t* degree);
+int poly_evaluate_multi(kzg_ctx* ctx, const Fr* const* polys, const uint64_t* lens, const Fr* points, uint32_t count,
+                        Fr* out_host);
+enum ScanKind { SCAN_ADD = 0, SCAN_MUL = 1 };
+int fr_exclusive_scan(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n, ScanKind kind, Fr* total_host);
+int poly_div_x_sub(kzg_ctx* ctx, const Fr* a, uint64_t n, const Fr& v, Fr* out, bool* exact);
+int poly_linear_combination(kzg_ctx* ctx, Fr* out, uint64_t n_out, const Fr* const* polys, const uint64_t* lens,
+                            const Fr* coeffs, uint32_t count, const Fr& constant);
+int grand_terms(kzg_ctx* ctx, int kind, const Fr* ev_f, const Fr* ev_t, const Fr* sel_f, const Fr* sel_t,
+                const Fr& gamma, Fr* num, Fr* den, uint64_t n);
+int fr_mul_pointwise(kzg_ctx* ctx, const Fr* a, const Fr* b, Fr* out, uint64_t n);
+int fr_fill(kzg_ctx* ctx, Fr* dst, uint64_t n, const Fr& v);
+// argument.cu
+int fr_scale_powers(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n, uint32_t log_order, bool inverse, const Fr* post);
+int grand_build(kzg_ctx* ctx, int kind, const Fr* ev_f, const Fr* ev_t, const Fr* sel_f, const Fr* sel_t, const Fr& gamma,
+                uint64_t n, Fr* acc, bool* wrap_ok);
+
+// host-side scalar helpers (tiny O(1)/O(log n) field work of the protocol drivers; the same
+// field.cuh code compiled for the host)
+Fr fr_from_bytes(const uint8_t b[32]);
+void fr_to_bytes(const Fr& a, uint8_t b[32]);
+Fr fr_root_of_unity(uint32_t log_n);  // Montgomery form, ffjavascript Fr.w[log_n]
+
+}  // namespace kzg

@@ -1,0 +1,421 @@
+// Context, device buffers and the bulk-Fr / Polynomial C ABI of libkzgb200.so.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace kzg {
+
+int set_err(kzg_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int ctx_scratch(kzg_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->scratch_bytes) {
+        // stream-ordered free of the old block, then a fresh (larger) one; rounded up to limit regrowth
+        if (ctx->scratch) {
+            KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            KZG_CUDA(ctx, cudaFree(ctx->scratch));
+            ctx->scratch = nullptr;
+            ctx->scratch_bytes = 0;
+        }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&ctx->scratch, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            e = cudaMalloc(&ctx->scratch, want);
+        }
+        if (e != cudaSuccess) return set_err(ctx, KZG_ERR_NOMEM, std::string("scratch allocation failed: ") + cudaGetErrorString(e));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return KZG_OK;
+}
+
+int buf_new(kzg_ctx* ctx, uint64_t n, bool zero, kzg_buf** out) {
+    kzg_buf* b = new kzg_buf();
+    b->n = n;
+    if (n) {
+        cudaError_t e = cudaMallocAsync((void**)&b->d, sizeof(Fr) * n, ctx->stream);
+        if (e != cudaSuccess) {
+            delete b;
+            return set_err(ctx, KZG_ERR_NOMEM, std::string("device allocation failed: ") + cudaGetErrorString(e));
+        }
+        if (zero) {
+            e = cudaMemsetAsync(b->d, 0, sizeof(Fr) * n, ctx->stream);
+            if (e != cudaSuccess) {
+                cudaFreeAsync(b->d, ctx->stream);
+                delete b;
+                return set_err(ctx, KZG_ERR_CUDA, cudaGetErrorString(e));
+            }
+        }
+    }
+    *out = b;
+    return KZG_OK;
+}
+
+// ---- self test kernels --------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix(uint64_t& s) {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <class P> __device__ Fp<P> random_fp(uint64_t& s) {
+    Fp<P> r;
+    for (int i = 0; i < 8; i += 2) {
+        uint64_t z = splitmix(s);
+        r.l[i] = (uint32_t)z;
+        r.l[i + 1] = (uint32_t)(z >> 32);
+    }
+    r.l[7] &= 0x1fffffffu;  // < 2^253 < p
+    return r;
+}
+template <class P> __device__ bool selftest_field(uint64_t& s) {
+    Fp<P> a = random_fp<P>(s), b = random_fp<P>(s), c = random_fp<P>(s);
+    bool ok = true;
+    ok &= fp_eq(fp_mul(a, b), fp_mul_portable(a, b));
+    ok &= fp_eq(fp_mul(a, a), fp_mul_portable(a, a));
+    ok &= fp_eq(fp_mul(fp_add(a, b), c), fp_add(fp_mul(a, c), fp_mul(b, c)));
+    ok &= fp_eq(fp_sub(fp_add(a, b), b), a);
+    ok &= fp_eq(fp_from_mont(fp_to_mont(a)), a);
+    return ok;
+}
+__global__ void selftest_kernel(uint32_t n, unsigned int* fail) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = 0x1234567ull + 977ull * i;
+    bool ok = selftest_field<FqP>(s) && selftest_field<FrP>(s);
+    // edge operands: p-1, 0, 1
+    Fq m1 = fp_neg(fp_one<FqP>());
+    ok &= fp_eq(fp_mul(m1, m1), fp_one<FqP>());
+    ok &= fp_eq(fp_mul(m1, m1), fp_mul_portable(m1, m1));
+    ok &= fp_is_zero(fp_mul(fp_zero<FqP>(), m1));
+    if ((i & 63) == 0) {
+        Fq a = random_fp<FqP>(s);
+        if (!fp_is_zero(a)) ok &= fp_eq(fp_mul(a, fp_inv(a)), fp_one<FqP>());
+        // group law on the generator (1, 2): 2G + G == G + G + G, (G + G) via madd hits the doubling branch
+        G1Affine g;
+        g.x = fp_one<FqP>();
+        g.y = fp_dbl(fp_one<FqP>());
+        ok &= g1_affine_on_curve(g);
+        G1XYZZ x = xyzz_inf();
+        xyzz_madd(x, g);
+        xyzz_madd(x, g);          // doubling branch
+        G1XYZZ d = xyzz_dbl_affine(g);
+        G1Affine xa = xyzz_to_affine(x), da = xyzz_to_affine(d);
+        ok &= fp_eq(xa.x, da.x) && fp_eq(xa.y, da.y) && g1_affine_on_curve(xa);
+        xyzz_madd(x, g);          // 3G
+        G1XYZZ y = d;
+        xyzz_add(y, xyzz_from_affine(g));
+        G1Affine ya = xyzz_to_affine(y);
+        xa = xyzz_to_affine(x);
+        ok &= fp_eq(xa.x, ya.x) && fp_eq(xa.y, ya.y) && g1_affine_on_curve(xa);
+        xyzz_madd(x, g1_affine_neg(g));  // back to 2G
+        xa = xyzz_to_affine(x);
+        ok &= fp_eq(xa.x, da.x) && fp_eq(xa.y, da.y);
+        G1XYZZ z = xyzz_mul_small(xyzz_from_affine(g), 3);
+        G1Affine za = xyzz_to_affine(z);
+        ok &= fp_eq(za.x, ya.x) && fp_eq(za.y, ya.y);
+        G1XYZZ o = xyzz_from_affine(g);
+        xyzz_madd(o, g1_affine_neg(g));  // G - G = inf
+        ok &= xyzz_is_inf(o);
+    }
+    if (!ok) atomicAdd(fail, 1u);
+}
+
+}  // namespace kzg
+
+using namespace kzg;
+
+extern "C" {
+
+int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
+    if (!out) return KZG_ERR_ARG;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return KZG_ERR_CUDA;  // no CPU fallback
+    kzg_ctx* ctx = new kzg_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return KZG_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return KZG_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return KZG_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    ctx->pinned_bytes = 1 << 16;
+    ctx->dev_small_bytes = 1 << 16;
+    if (cudaMallocHost((void**)&ctx->pinned, ctx->pinned_bytes) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->dev_small, ctx->dev_small_bytes) != cudaSuccess) {
+        delete ctx;
+        return KZG_ERR_CUDA;
+    }
+    // keep freed stream-ordered allocations cached in the pool instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    int r = ntt_init_tables(ctx);
+    if (r != KZG_OK) {
+        delete ctx;
+        return r;
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        delete ctx;
+        return KZG_ERR_CUDA;
+    }
+    *out = ctx;
+    return KZG_OK;
+}
+
+int kzg_ctx_destroy(kzg_ctx* ctx) {
+    if (!ctx) return KZG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int d = 0; d < 2; d++) {
+        cudaFree(ctx->tw_lo[d]);
+        cudaFree(ctx->tw_hi[d]);
+    }
+    cudaFree(ctx->scratch);
+    cudaFree(ctx->dev_small);
+    cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return KZG_OK;
+}
+
+int kzg_ctx_sync(kzg_ctx* ctx) {
+    if (!ctx) return KZG_ERR_ARG;
+    KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KZG_OK;
+}
+
+const char* kzg_last_error(kzg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t kzg_ctx_launch_count(kzg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int kzg_selftest(kzg_ctx* ctx, uint32_t n_cases) {
+    if (!ctx) return KZG_ERR_ARG;
+    unsigned int* slot = (unsigned int*)ctx->dev_small;
+    KZG_CUDA(ctx, cudaMemsetAsync(slot, 0, sizeof(unsigned int), ctx->stream));
+    KZG_LAUNCH(ctx, selftest_kernel, (n_cases + 127) / 128, 128, 0, n_cases, slot);
+    KZG_CHECK_LAUNCH(ctx);
+    KZG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, slot, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned int fails;
+    memcpy(&fails, ctx->pinned, sizeof(fails));
+    if (fails) return set_err(ctx, KZG_ERR_CUDA, "device self-test failed in " + std::to_string(fails) + " cases");
+    return KZG_OK;
+}
+
+// ---- buffers ------------------------------------------------------------------------------------
+int kzg_buf_alloc(kzg_ctx* ctx, uint64_t n, kzg_buf** out) {
+    if (!ctx || !out) return KZG_ERR_ARG;
+    return buf_new(ctx, n, true, out);
+}
+int kzg_buf_free(kzg_ctx* ctx, kzg_buf* b) {
+    if (!ctx || !b) return KZG_OK;
+    if (b->d) cudaFreeAsync(b->d, ctx->stream);
+    delete b;
+    return KZG_OK;
+}
+uint64_t kzg_buf_len(kzg_buf* b) { return b ? b->n : 0; }
+void* kzg_buf_device_ptr(kzg_buf* b) { return b ? (void*)b->d : nullptr; }
+
+int kzg_buf_upload(kzg_ctx* ctx, kzg_buf* dst, uint64_t dst_off, const uint8_t* host, uint64_t n) {
+    if (!ctx || !dst || (!host && n)) return KZG_ERR_ARG;
+    if (dst_off + n > dst->n) return set_err(ctx, KZG_ERR_ARG, "upload out of bounds");
+    if (n == 0) return KZG_OK;
+    KZG_CUDA(ctx, cudaMemcpyAsync(dst->d + dst_off, host, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host buffer may be pageable / reused by the caller
+    return KZG_OK;
+}
+int kzg_buf_download(kzg_ctx* ctx, kzg_buf* src, uint64_t src_off, uint8_t* host, uint64_t n) {
+    if (!ctx || !src || (!host && n)) return KZG_ERR_ARG;
+    if (src_off + n > src->n) return set_err(ctx, KZG_ERR_ARG, "download out of bounds");
+    if (n == 0) return KZG_OK;
+    KZG_CUDA(ctx, cudaMemcpyAsync(host, src->d + src_off, sizeof(Fr) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KZG_OK;
+}
+int kzg_buf_copy(kzg_ctx* ctx, kzg_buf* dst, uint64_t dst_off, kzg_buf* src, uint64_t src_off, uint64_t n) {
+    if (!ctx || !dst || !src) return KZG_ERR_ARG;
+    if (dst_off + n > dst->n || src_off + n > src->n) return set_err(ctx, KZG_ERR_ARG, "copy out of bounds");
+    if (n == 0) return KZG_OK;
+    KZG_CUDA(ctx, cudaMemcpyAsync(dst->d + dst_off, src->d + src_off, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    return KZG_OK;
+}
+int kzg_buf_fill(kzg_ctx* ctx, kzg_buf* dst, uint64_t off, uint64_t n, const uint8_t value[32]) {
+    if (!ctx || !dst || !value) return KZG_ERR_ARG;
+    if (off + n > dst->n) return set_err(ctx, KZG_ERR_ARG, "fill out of bounds");
+    return fr_fill(ctx, dst->d + off, n, fr_from_bytes(value));
+}
+
+// ---- bulk Fr ------------------------------------------------------------------------------------
+int kzg_fr_to_mont(kzg_ctx* ctx, kzg_buf* in, kzg_buf* out) {
+    if (!ctx || !in || !out || in->n != out->n) return KZG_ERR_ARG;
+    return fr_convert(ctx, in->d, out->d, in->n, true);
+}
+int kzg_fr_from_mont(kzg_ctx* ctx, kzg_buf* in, kzg_buf* out) {
+    if (!ctx || !in || !out || in->n != out->n) return KZG_ERR_ARG;
+    return fr_convert(ctx, in->d, out->d, in->n, false);
+}
+static int log2_exact(uint64_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int l = 0;
+    while ((1ull << l) < n) l++;
+    return l;
+}
+int kzg_fr_ntt(kzg_ctx* ctx, kzg_buf* in, kzg_buf* out, int inverse) {
+    if (!ctx || !in || !out || in->n != out->n) return KZG_ERR_ARG;
+    int lg = log2_exact(in->n);
+    if (lg < 0) return set_err(ctx, KZG_ERR_PROTOCOL, "fft must be multiple of 2");
+    return ntt_run(ctx, in->d, in->n, out->d, (uint32_t)lg, inverse != 0);
+}
+int kzg_fr_extend_ntt(kzg_ctx* ctx, kzg_buf* coef, uint32_t extension, kzg_buf** out) {
+    if (!ctx || !coef || !out || extension == 0 || (extension & (extension - 1))) return KZG_ERR_ARG;
+    uint32_t power = 0;
+    while ((1ull << power) < coef->n) power++;
+    uint64_t len = (1ull << power) * extension;
+    int lg = log2_exact(len);
+    kzg_buf* o = nullptr;
+    KZG_TRY(buf_new(ctx, len, false, &o));
+    int r = ntt_run(ctx, coef->d, coef->n, o->d, (uint32_t)lg, false);
+    if (r != KZG_OK) {
+        kzg_buf_free(ctx, o);
+        return r;
+    }
+    *out = o;
+    return KZG_OK;
+}
+int kzg_fr_batch_inverse(kzg_ctx* ctx, kzg_buf* in, kzg_buf* out) {
+    if (!ctx || !in || !out || in->n != out->n) return KZG_ERR_ARG;
+    return fr_batch_inverse(ctx, in->d, out->d, in->n);
+}
+
+// ---- Polynomial ---------------------------------------------------------------------------------
+static int poly_addsub(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out, bool sub) {
+    if (!ctx || !a || !b || !out) return KZG_ERR_ARG;
+    uint64_t n = a->n > b->n ? a->n : b->n;
+    kzg_buf* o = nullptr;
+    KZG_TRY(buf_new(ctx, n, false, &o));
+    const Fr* polys[2] = {a->d, b->d};
+    uint64_t lens[2] = {a->n, b->n};
+    Fr coeffs[2] = {fp_one<FrP>(), sub ? fp_neg(fp_one<FrP>()) : fp_one<FrP>()};
+    int r = poly_linear_combination(ctx, o->d, n, polys, lens, coeffs, 2, fp_zero<FrP>());
+    if (r != KZG_OK) {
+        kzg_buf_free(ctx, o);
+        return r;
+    }
+    *out = o;
+    return KZG_OK;
+}
+int kzg_poly_add(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) { return poly_addsub(ctx, a, b, out, false); }
+int kzg_poly_sub(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) { return poly_addsub(ctx, a, b, out, true); }
+
+int kzg_poly_mul_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32]) {
+    if (!ctx || !a || !s) return KZG_ERR_ARG;
+    const Fr* polys[1] = {a->d};
+    uint64_t lens[1] = {a->n};
+    Fr coeffs[1] = {fr_from_bytes(s)};
+    return poly_linear_combination(ctx, a->d, a->n, polys, lens, coeffs, 1, fp_zero<FrP>());
+}
+static int poly_addsub_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32], bool sub) {
+    if (!ctx || !a || !s) return KZG_ERR_ARG;
+    if (a->n == 0) return set_err(ctx, KZG_ERR_ARG, "addScalar on an empty polynomial");
+    const Fr* polys[1] = {a->d};
+    uint64_t lens[1] = {1};
+    Fr coeffs[1] = {fp_one<FrP>()};
+    Fr c = fr_from_bytes(s);
+    if (sub) c = fp_neg(c);
+    return poly_linear_combination(ctx, a->d, 1, polys, lens, coeffs, 1, c);
+}
+int kzg_poly_add_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32]) { return poly_addsub_scalar(ctx, a, s, false); }
+int kzg_poly_sub_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32]) { return poly_addsub_scalar(ctx, a, s, true); }
+
+int kzg_poly_degree(kzg_ctx* ctx, kzg_buf* a, uint64_t* degree) {
+    if (!ctx || !a || !degree) return KZG_ERR_ARG;
+    return poly_degree(ctx, a->d, a->n, degree);
+}
+int kzg_poly_evaluate(kzg_ctx* ctx, kzg_buf* a, const uint8_t x[32], uint8_t out[32]) {
+    if (!ctx || !a || !x || !out) return KZG_ERR_ARG;
+    const Fr* polys[1] = {a->d};
+    uint64_t lens[1] = {a->n};
+    Fr pts[1] = {fr_from_bytes(x)};
+    Fr res;
+    KZG_TRY(poly_evaluate_multi(ctx, polys, lens, pts, 1, &res));
+    fr_to_bytes(res, out);
+    return KZG_OK;
+}
+int kzg_poly_multiply(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) {
+    if (!ctx || !a || !b || !out) return KZG_ERR_ARG;
+    uint64_t da = 0, db = 0;
+    KZG_TRY(poly_degree(ctx, a->d, a->n, &da));
+    KZG_TRY(poly_degree(ctx, b->d, b->n, &db));
+    uint32_t lg = 0;
+    while ((1ull << lg) < da + db + 1) lg++;
+    const uint64_t len = 1ull << lg;
+    kzg_buf *fa = nullptr, *fb = nullptr;
+    KZG_TRY(buf_new(ctx, len, false, &fa));
+    KZG_TRY(buf_new(ctx, len, false, &fb));
+    int r = ntt_run(ctx, a->d, da + 1 < a->n ? da + 1 : a->n, fa->d, lg, false);
+    if (r == KZG_OK) r = ntt_run(ctx, b->d, db + 1 < b->n ? db + 1 : b->n, fb->d, lg, false);
+    if (r == KZG_OK) r = fr_mul_pointwise(ctx, fa->d, fb->d, fa->d, len);
+    if (r == KZG_OK) r = ntt_run(ctx, fa->d, len, fb->d, lg, true);
+    kzg_buf_free(ctx, fa);
+    if (r != KZG_OK) {
+        kzg_buf_free(ctx, fb);
+        return r;
+    }
+    *out = fb;
+    return KZG_OK;
+}
+int kzg_poly_lagrange1(kzg_ctx* ctx, uint32_t power, kzg_buf** out) {
+    if (!ctx || !out || power > 26) return KZG_ERR_ARG;
+    // iNTT of e_0: every coefficient equals n^-1
+    Fr n = fp_zero<FrP>();
+    uint64_t N = 1ull << power;
+    n.l[0] = (uint32_t)N;
+    n.l[1] = (uint32_t)(N >> 32);
+    Fr ninv = fp_inv(fp_to_mont(n));
+    kzg_buf* o = nullptr;
+    KZG_TRY(buf_new(ctx, N, false, &o));
+    int r = fr_fill(ctx, o->d, N, ninv);
+    if (r != KZG_OK) {
+        kzg_buf_free(ctx, o);
+        return r;
+    }
+    *out = o;
+    return KZG_OK;
+}
+int kzg_poly_div_x_sub_value(kzg_ctx* ctx, kzg_buf* a, const uint8_t v[32], kzg_buf** out) {
+    if (!ctx || !a || !v || !out) return KZG_ERR_ARG;
+    if (a->n < 2) return set_err(ctx, KZG_ERR_ARG, "divByXSubValue needs at least two coefficients");
+    kzg_buf* o = nullptr;
+    KZG_TRY(buf_new(ctx, a->n, false, &o));
+    bool exact = false;
+    int r = poly_div_x_sub(ctx, a->d, a->n, fr_from_bytes(v), o->d, &exact);
+    if (r == KZG_OK && !exact) r = set_err(ctx, KZG_ERR_PROTOCOL, "Polynomial does not divide");
+    if (r != KZG_OK) {
+        kzg_buf_free(ctx, o);
+        return r;
+    }
+    *out = o;
+    return KZG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+// BN254 Fq / Fr arithmetic: 8 x 32-bit limbs, Montgomery form (R = 2^256), fully reduced outputs.
+//
+// In-memory form is exactly the reference's: 32-byte little-endian Montgomery residue
+// (ffjavascript Fr/Fq elements), so device buffers are byte-compatible with the
+// `.coef` / `.eval` / ptau section-2 bytes and no transposition is needed at the boundary.
+//
+// Two multiplication paths:
+//   * fp_mul_portable : operand-scanning CIOS with 64-bit temporaries; host + device; the
+//     specification, unit-tested on the CPU against Python big ints.
+//   * fp_mul (device) : even/odd split accumulators with mad.lo.cc / madc.hi.cc carry chains
+//     (each lo/hi pair is one IMAD.WIDE.U32 with carry in SASS on sm_100a) -- 128 wide MACs
+//     for the product + reduction, 8 IMAD for the quotient digits.  Checked against the
+//     portable path on the device by kzg_selftest().
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KZG_HD __host__ __device__ __forceinline__
+#define KZG_D __device__ __forceinline__
+#else
+#define KZG_HD inline
+#define KZG_D inline
+#endif
+
+#ifndef KZG_FAST_MUL
+#define KZG_FAST_MUL 1
+#endif
+
+namespace kzg {
+
+struct FqP {
+    static constexpr uint32_t INV = 0xe4866389u;  // -q^-1 mod 2^32
+    KZG_HD static constexpr uint32_t mod(int i) {
+        return i == 0 ? 0xd87cfd47u : i == 1 ? 0x3c208c16u : i == 2 ? 0x6871ca8du : i == 3 ? 0x97816a91u
+             : i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+    }
+    KZG_HD static constexpr uint32_t r1(int i) {  // R mod q  (Montgomery one)
+        return i == 0 ? 0xc58f0d9du : i == 1 ? 0xd35d438du : i == 2 ? 0xf5c70b3du : i == 3 ? 0x0a78eb28u
+             : i == 4 ? 0x7879462cu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+    }
+    KZG_HD static constexpr uint32_t r2(int i) {  // R^2 mod q
+        return i == 0 ? 0x538afa89u : i == 1 ? 0xf32cfc5bu : i == 2 ? 0xd44501fbu : i == 3 ? 0xb5e71911u
+             : i == 4 ? 0x0a417ff6u : i == 5 ? 0x47ab1effu : i == 6 ? 0xcab8351fu : 0x06d89f71u;
+    }
+};
+
+struct FrP {
+    static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32
+    KZG_HD static constexpr uint32_t mod(int i) {
+        return i == 0 ? 0xf0000001u : i == 1 ? 0x43e1f593u : i == 2 ? 0x79b97091u : i == 3 ? 0x2833e848u
+             : i == 4 ? 0x8181585du : i == 5 ? 0xb85045b6u : i == 6 ? 0xe131a029u : 0x30644e72u;
+    }
+    KZG_HD static constexpr uint32_t r1(int i) {
+        return i == 0 ? 0x4ffffffbu : i == 1 ? 0xac96341cu : i == 2 ? 0x9f60cd29u : i == 3 ? 0x36fc7695u
+             : i == 4 ? 0x7879462eu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
+    }
+    KZG_HD static constexpr uint32_t r2(int i) {
+        return i == 0 ? 0xae216da7u : i == 1 ? 0x1bb8e645u : i == 2 ? 0xe35c59e3u : i == 3 ? 0x53fe3ab1u
+             : i == 4 ? 0x53bb8085u : i == 5 ? 0x8c49833du : i == 6 ? 0x7f4e44a5u : 0x0216d0b1u;
+    }
+};
+
+template <class P>
+struct alignas(16) Fp {
+    uint32_t l[8];
+};
+using Fq = Fp<FqP>;
+using Fr = Fp<FrP>;
+
+// ------------------------------------------------------------------------------------------------
+// constants, predicates, load/store
+// ------------------------------------------------------------------------------------------------
+template <class P> KZG_HD Fp<P> fp_zero() {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = 0;
+    return r;
+}
+template <class P> KZG_HD Fp<P> fp_one() {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::r1(i);
+    return r;
+}
+template <class P> KZG_HD Fp<P> fp_r2() {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::r2(i);
+    return r;
+}
+template <class P> KZG_HD bool fp_is_zero(const Fp<P>& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= a.l[i];
+    return o == 0;
+}
+template <class P> KZG_HD bool fp_eq(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= a.l[i] ^ b.l[i];
+    return o == 0;
+}
+// a >= p ?
+template <class P> KZG_HD bool fp_geq_mod(const uint32_t* a) {
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        if (a[i] > P::mod(i)) return true;
+        if (a[i] < P::mod(i)) return false;
+    }
+    return true;
+}
+
+template <class P> KZG_HD Fp<P> fp_load(const void* p) {
+    Fp<P> r;
+#if defined(__CUDA_ARCH__)
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+#else
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    for (int i = 0; i < 8; i++) r.l[i] = q[i];
+#endif
+    return r;
+}
+template <class P> KZG_HD void fp_store(void* p, const Fp<P>& r) {
+#if defined(__CUDA_ARCH__)
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
+    q[1] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
+#else
+    uint32_t* q = reinterpret_cast<uint32_t*>(p);
+    for (int i = 0; i < 8; i++) q[i] = r.l[i];
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// add / sub / neg / dbl  (inputs < p, outputs < p)
+// ------------------------------------------------------------------------------------------------
+template <class P> KZG_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> s, d;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;\n\t"
+        : "=r"(s.l[0]), "=r"(s.l[1]), "=r"(s.l[2]), "=r"(s.l[3]), "=r"(s.l[4]), "=r"(s.l[5]), "=r"(s.l[6]), "=r"(s.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    // p < 2^254 so a + b < 2^255: no carry out of limb 7.  d = s - p, keep d if no borrow.
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;\n\t"
+        : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7]),
+          "=r"(borrow)
+        : "r"(s.l[0]), "r"(s.l[1]), "r"(s.l[2]), "r"(s.l[3]), "r"(s.l[4]), "r"(s.l[5]), "r"(s.l[6]), "r"(s.l[7]),
+          "r"(P::mod(0)), "r"(P::mod(1)), "r"(P::mod(2)), "r"(P::mod(3)), "r"(P::mod(4)), "r"(P::mod(5)), "r"(P::mod(6)), "r"(P::mod(7)));
+#pragma unroll
+    for (int i = 0; i < 8; i++) d.l[i] = borrow ? s.l[i] : d.l[i];
+    return d;
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a.l[i] + b.l[i];
+        s.l[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    int64_t bw = 0;
+    for (int i = 0; i < 8; i++) {
+        bw += (int64_t)s.l[i] - (int64_t)P::mod(i);
+        d.l[i] = (uint32_t)bw;
+        bw >>= 32;
+    }
+    return bw ? s : d;
+#endif
+}
+
+template <class P> KZG_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> d;
+#if defined(__CUDA_ARCH__)
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;\n\t"
+        : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7]),
+          "=r"(borrow)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    // borrow is 0 or 0xffffffff: add (p & borrow)
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;\n\t"
+        : "+r"(d.l[0]), "+r"(d.l[1]), "+r"(d.l[2]), "+r"(d.l[3]), "+r"(d.l[4]), "+r"(d.l[5]), "+r"(d.l[6]), "+r"(d.l[7])
+        : "r"(P::mod(0) & borrow), "r"(P::mod(1) & borrow), "r"(P::mod(2) & borrow), "r"(P::mod(3) & borrow),
+          "r"(P::mod(4) & borrow), "r"(P::mod(5) & borrow), "r"(P::mod(6) & borrow), "r"(P::mod(7) & borrow));
+    return d;
+#else
+    int64_t bw = 0;
+    for (int i = 0; i < 8; i++) {
+        bw += (int64_t)a.l[i] - (int64_t)b.l[i];
+        d.l[i] = (uint32_t)bw;
+        bw >>= 32;
+    }
+    if (bw) {
+        uint64_t c = 0;
+        for (int i = 0; i < 8; i++) {
+            c += (uint64_t)d.l[i] + P::mod(i);
+            d.l[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    return d;
+#endif
+}
+
+template <class P> KZG_HD Fp<P> fp_neg(const Fp<P>& a) {
+    return fp_sub(fp_zero<P>(), a);
+}
+template <class P> KZG_HD Fp<P> fp_dbl(const Fp<P>& a) {
+    return fp_add(a, a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Montgomery multiplication
+// ------------------------------------------------------------------------------------------------
+// final conditional subtraction: t in [0, 2p) -> [0, p)
+template <class P> KZG_HD Fp<P> fp_final_sub(const uint32_t* t) {
+    Fp<P> s, d;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s.l[i] = t[i];
+#if defined(__CUDA_ARCH__)
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;\n\t"
+        : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7]),
+          "=r"(borrow)
+        : "r"(s.l[0]), "r"(s.l[1]), "r"(s.l[2]), "r"(s.l[3]), "r"(s.l[4]), "r"(s.l[5]), "r"(s.l[6]), "r"(s.l[7]),
+          "r"(P::mod(0)), "r"(P::mod(1)), "r"(P::mod(2)), "r"(P::mod(3)), "r"(P::mod(4)), "r"(P::mod(5)), "r"(P::mod(6)), "r"(P::mod(7)));
+#pragma unroll
+    for (int i = 0; i < 8; i++) d.l[i] = borrow ? s.l[i] : d.l[i];
+    return d;
+#else
+    int64_t bw = 0;
+    for (int i = 0; i < 8; i++) {
+        bw += (int64_t)s.l[i] - (int64_t)P::mod(i);
+        d.l[i] = (uint32_t)bw;
+        bw >>= 32;
+    }
+    return bw ? s : d;
+#endif
+}
+
+template <class P> KZG_HD Fp<P> fp_mul_portable(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c += (uint64_t)a.l[j] * b.l[i] + t[j];
+            t[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[8] = (uint32_t)c;
+        t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * P::INV;
+        c = (uint64_t)m * P::mod(0) + t[0];
+        c >>= 32;
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            c += (uint64_t)m * P::mod(j) + t[j];
+            t[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[7] = (uint32_t)c;
+        t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    return fp_final_sub<P>(t);
+}
+
+#if defined(__CUDA_ARCH__)
+// ---- even/odd carry-chain building blocks (device only) ----------------------------------------
+// acc[0..7] += {x0, x2, x4, x6} * y over limb positions 0..7 (one carry chain); the carry out of the
+// chain is added to `top` (the word above, which lives in the *other* accumulator).
+KZG_D void cmad4_top(uint32_t* acc, uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y, uint32_t& top) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+          "+r"(top)
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+}
+// same, carry out dropped (provably zero by the 2p bound)
+KZG_D void cmad4(uint32_t* acc, uint32_t x0, uint32_t x2, uint32_t x4, uint32_t x6, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;\n\t"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+}
+// lo[0] += carry_word (a word sitting at the same limb position in the other accumulator), then
+// hi[j] = {x1,x3,x5,x7} * y + hi[j+2] (j = 0,2,4), hi[6,7] = x7*y + carry : the one-limb right
+// shift of the accumulator pair after a reduction step, fused with the next row of products.
+KZG_D void shift_mad4(uint32_t& lo0, uint32_t carry_word, uint32_t* hi, uint32_t x1, uint32_t x3, uint32_t x5, uint32_t x7, uint32_t y) {
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "madc.lo.cc.u32 %1, %10, %14, %3;\n\t"
+        "madc.hi.cc.u32 %2, %10, %14, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %14, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %14, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %14, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %14, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %14, 0;\n\t"
+        "madc.hi.u32 %8, %13, %14, 0;\n\t"
+        : "+r"(lo0), "+r"(hi[0]), "+r"(hi[1]), "+r"(hi[2]), "+r"(hi[3]), "+r"(hi[4]), "+r"(hi[5]), "+r"(hi[6]), "+r"(hi[7])
+        : "r"(carry_word), "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+}
+#endif
+
+// Even/odd Montgomery product.  `lo` holds limb positions 0..7, `hi` holds positions 1..8 of the
+// running total; after each reduction step the total is divisible by 2^32, the pair is shifted one
+// limb (roles swap: hi becomes the new lo) and the old lo, shifted by two limbs, is re-used as the
+// new hi while the next row of odd products is accumulated into it.
+template <class P> KZG_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__) && KZG_FAST_MUL
+    uint32_t x[8], y[8];  // x: positions 0..7 ("lo"), y: positions 1..8 ("hi")
+    // row 0: plain products
+    asm("mul.lo.u32 %0, %8, %12;\n\t mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t mul.hi.u32 %7, %11, %12;\n\t"
+        : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+        : "r"(a.l[0]), "r"(a.l[2]), "r"(a.l[4]), "r"(a.l[6]), "r"(b.l[0]));
+    asm("mul.lo.u32 %0, %8, %12;\n\t mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t mul.hi.u32 %7, %11, %12;\n\t"
+        : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7])
+        : "r"(a.l[1]), "r"(a.l[3]), "r"(a.l[5]), "r"(a.l[7]), "r"(b.l[0]));
+    {
+        uint32_t m = x[0] * P::INV;
+        cmad4(y, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+        cmad4_top(x, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m, y[7]);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        // roles: on odd i the pair is (lo = y, hi = x); on even i it is (lo = x, hi = y)
+        uint32_t* lo = (i & 1) ? y : x;
+        uint32_t* hi = (i & 1) ? x : y;
+        // old-lo word 1 sits at the new position 0; old-lo words 2..7 become the new hi words 0..5
+        shift_mad4(lo[0], hi[1], hi, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+        cmad4_top(lo, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i], hi[7]);
+        uint32_t m = lo[0] * P::INV;
+        cmad4(hi, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+        cmad4_top(lo, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m, hi[7]);
+    }
+    // after row 7 (odd): lo = y, hi = x.  result word j = hi[j] + lo[j+1] (lo[0] == 0)
+    uint32_t t[8];
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, 0;\n\t"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]),
+          "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]));
+    return fp_final_sub<P>(t);
+#else
+    return fp_mul_portable(a, b);
+#endif
+}
+
+template <class P> KZG_HD Fp<P> fp_sqr(const Fp<P>& a) {
+    return fp_mul(a, a);
+}
+
+template <class P> KZG_HD Fp<P> fp_to_mont(const Fp<P>& a) {
+    return fp_mul(a, fp_r2<P>());
+}
+template <class P> KZG_HD Fp<P> fp_from_mont(const Fp<P>& a) {
+    Fp<P> one = fp_zero<P>();
+    one.l[0] = 1;
+    return fp_mul(a, one);
+}
+
+// a^e, e given as 8 little-endian 32-bit limbs (plain integer)
+template <class P> KZG_HD Fp<P> fp_pow(const Fp<P>& a, const uint32_t* e) {
+    Fp<P> r = fp_one<P>();
+    bool started = false;
+    for (int i = 7; i >= 0; i--) {
+        for (int bit = 31; bit >= 0; bit--) {
+            if (started) r = fp_sqr(r);
+            if ((e[i] >> bit) & 1) {
+                r = started ? fp_mul(r, a) : a;
+                started = true;
+            }
+        }
+    }
+    return r;
+}
+template <class P> KZG_HD Fp<P> fp_pow_u64(const Fp<P>& a, uint64_t e) {
+    uint32_t ee[8] = {(uint32_t)e, (uint32_t)(e >> 32), 0, 0, 0, 0, 0, 0};
+    return fp_pow(a, ee);
+}
+// a^-1 = a^(p-2); inv(0) = 0
+template <class P> KZG_HD Fp<P> fp_inv(const Fp<P>& a) {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+    e[0] -= 2;  // mod(0) >= 2 for both fields, no borrow
+    return fp_pow(a, e);
+}
+
+}  // namespace kzg

@@ -1,0 +1,109 @@
+"""Evaluations: evaluation-form vector, mirror of reference src/polynomial/evaluations.js:5-138.
+
+`eval` is either host bytes (what callers construct, e.g. getRandomEvals) or a device buffer (what the
+library returns); bulk work runs on the device through the C ABI.
+"""
+import ctypes as C
+import random as _random
+
+from ..curve import DeviceBuffer
+from .._lib import as_ptr
+
+
+class Evaluations:
+    def __init__(self, evaluations, curve):                     # evaluations.js:6-10
+        self.eval = evaluations
+        self.curve = curve
+        self.Fr = curve.Fr
+
+    # ---- constructors -------------------------------------------------------------------------------
+    @staticmethod
+    def fromPolynomial(polynomial, extension, curve):           # evaluations.js:12-21
+        out = C.c_void_p()
+        coef = curve.to_device(polynomial.coef)
+        curve.check(curve.lib.kzg_fr_extend_ntt(curve.ctx, coef.handle, extension, C.byref(out)))
+        return Evaluations(curve.wrap(out), curve)
+
+    @staticmethod
+    def fromArray(array, curve):                                # evaluations.js:23-29
+        return Evaluations(b"".join(bytes(a) for a in array), curve)
+
+    @staticmethod
+    def fromEvals(evals):                                       # evaluations.js:31-33
+        return Evaluations(evals.tobytes(), evals.curve)
+
+    @staticmethod
+    def getOneEvals(length, curve):                             # evaluations.js:35-41
+        return Evaluations(curve.Fr.one * length, curve)
+
+    @staticmethod
+    def getZeroEvals(length, curve):                            # evaluations.js:43-49
+        return Evaluations(bytes(32 * length), curve)
+
+    @staticmethod
+    def getRandomEvals(length, curve):                          # evaluations.js:51-57
+        return Evaluations(b"".join(curve.Fr.random() for _ in range(length)), curve)
+
+    @staticmethod
+    def getRandomBinEvals(length, curve):                       # evaluations.js:59-66
+        return Evaluations(b"".join(curve.Fr.one if _random.getrandbits(1) else curve.Fr.zero for _ in range(length)), curve)
+
+    # ---- accessors ----------------------------------------------------------------------------------
+    def tobytes(self):
+        return self.eval.tobytes() if isinstance(self.eval, DeviceBuffer) else bytes(self.eval)
+
+    def getEvaluation(self, index):                             # evaluations.js:68-74
+        if (index + 1) * 32 > self.length() * 32:
+            raise IndexError("Evaluations.getEvaluation() out of bounds")
+        if isinstance(self.eval, DeviceBuffer):
+            return self.eval.slice(index * 32, (index + 1) * 32)
+        return bytes(self.eval[index * 32:(index + 1) * 32])
+
+    def getEvaluationSequence(self, start, end):                # evaluations.js:76-88
+        if start > end:
+            raise IndexError("Evaluations.getEvaluationSequence() start index is greater than end index")
+        if start == end:
+            raise IndexError("Use Evaluations.getEvaluation() instead")
+        if end > self.length() - 1:
+            raise IndexError("Evaluations.getEvaluationSequence() end index is out of bounds")
+        if isinstance(self.eval, DeviceBuffer):
+            return self.eval.slice(start * 32, end * 32)
+        return bytes(self.eval[start * 32:end * 32])
+
+    def setEvaluation(self, index, value):                      # evaluations.js:90-96
+        if index > self.length() - 1:
+            raise IndexError("Evaluation index is out of bounds")
+        if isinstance(self.eval, DeviceBuffer):
+            self.curve.check(self.curve.lib.kzg_buf_upload(self.curve.ctx, self.eval.handle, index, as_ptr(bytes(value)), 1))
+        else:
+            b = bytearray(self.eval)
+            b[index * 32:(index + 1) * 32] = bytes(value)
+            self.eval = b
+
+    def length(self):                                           # evaluations.js:99-108
+        nbytes = self.eval.byteLength if isinstance(self.eval, DeviceBuffer) else len(self.eval)
+        if nbytes % 32:
+            raise ValueError("Polynomial evaluations buffer has incorrect size")
+        return nbytes // 32
+
+    def isEqual(self, other):                                   # evaluations.js:110-116
+        if self.length() != other.length():
+            return False
+        return self.tobytes() == other.tobytes()
+
+    def _all_equal(self, value):
+        if isinstance(self.eval, DeviceBuffer):
+            out = C.c_int()
+            self.curve.check(self.curve.lib.kzg_buf_all_equal(self.curve.ctx, self.eval.handle, as_ptr(value), C.byref(out)))
+            return bool(out.value)
+        return bytes(self.eval) == value * self.length()
+
+    def isAllZeros(self):                                       # evaluations.js:118-121
+        return self._all_equal(self.Fr.zero)
+
+    def isAllOnes(self):                                        # evaluations.js:123-129
+        return self._all_equal(self.Fr.one)
+
+    def print(self, name="f"):                                  # evaluations.js:131-135
+        for i in range(self.length()):
+            print("%s(w^%d) = %s" % (name, i, self.Fr.toString(self.getEvaluation(i))))
