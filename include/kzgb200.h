@@ -54,6 +54,15 @@ const char* kzg_last_error(kzg_ctx* ctx);
 uint64_t kzg_ctx_launch_count(kzg_ctx* ctx);
 /* device self-test: fast Montgomery path == portable path, group law identities.  0 = pass */
 int kzg_selftest(kzg_ctx* ctx, uint32_t n_cases);
+/* roofline denominator for the integer kernels: measured throughput of independent 32x32+64 -> 64 bit
+ * multiply-accumulate chains (IMAD.WIDE.U32 in SASS), in MAC/s, over `ms` milliseconds of kernel time */
+int kzg_bench_imad_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second);
+/* same unit, measured on chains of this library's own Montgomery product (136 limb-MACs each): the practical
+ * ceiling once the carry handling (IADD3) and the quotient-digit IMADs of a modular product are included */
+int kzg_bench_modmul_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second);
+/* device time in milliseconds the context's kernels tagged `which` took since the last reset (CUDA events
+ * on the context's stream; 0 = msm bucket accumulation).  Used by bench.py for the live roofline figure. */
+int kzg_ctx_kernel_time(kzg_ctx* ctx, uint32_t which, int reset, double* ms_out, uint64_t* launches_out);
 
 /* ---- SRS ---------------------------------------------------------------------------------------------- */
 /* replaces readBinFile + readPTauHeader + fd.readToBuffer (prover.js:15-16,83-85; ptau_utils.js:3-24):
@@ -68,11 +77,14 @@ int kzg_srs_from_host(kzg_ctx* ctx, const uint8_t* affine, uint64_t n_points, kz
 /* synthetic SRS: [tau^i]_1 for i < n_points computed on the device (the Hermez file of
  * .github/workflows/tests.yml:15-19 cannot be downloaded offline).  tau_std = 32 B standard-form LE. */
 int kzg_srs_generate(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t n_points, kzg_srs** out);
+/* the slice [tau^i]_1, first <= i < first + n_points: the shard of one GPU in the multi-GPU MSM */
+int kzg_srs_generate_range(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t first, uint64_t n_points, kzg_srs** out);
 /* write a .ptau (sections 1,2,3) from a device SRS; tau_g2 = 128 B [tau]_2 (host computed by the caller) */
 int kzg_srs_write_ptau(kzg_ctx* ctx, kzg_srs* srs, uint32_t power, const uint8_t g2_one[128],
                        const uint8_t g2_tau[128], const char* path);
 int kzg_srs_download(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, uint64_t count, uint8_t* out);
 uint64_t kzg_srs_len(kzg_srs* srs);
+void* kzg_srs_device_ptr(kzg_srs* srs); /* device address of the 64-byte affine points (for KZG_BASES_ON_DEVICE) */
 int kzg_srs_free(kzg_ctx* ctx, kzg_srs* srs);
 
 /* ---- device Fr vectors (BigBuffer / Uint8Array of n*32 bytes) ---------------------------------------- */
@@ -135,7 +147,9 @@ int kzg_srs_msm(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std
  * partials, kzg_g1_partials_combine adds `count` of them and returns the affine point. */
 int kzg_srs_msm_partial(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std, uint64_t n, void* partial_dev);
 int kzg_g1_partials_combine(kzg_ctx* ctx, const void* partials_dev, uint32_t count, uint8_t out_affine[64]);
-/* MSM tuning: window bits (0 = auto from n) */
+/* MSM tuning: window bits (0 = auto from n); kzg_msm_geometry reports what an n-point MSM will use
+ * (montgomery = 1 for kzg_commit's scalars, 0 for standard-form scalars) */
+int kzg_msm_geometry(kzg_ctx* ctx, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows);
 int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c);
 
 /* ---- fused provers (prover.js:144-413 and the grand-product twin) --------------------------------------- */

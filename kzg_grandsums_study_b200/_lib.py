@@ -24,14 +24,19 @@ SIGNATURES = {
     "kzg_last_error": (C.c_char_p, [vp]),
     "kzg_ctx_launch_count": (u64, [vp]),
     "kzg_selftest": (i32, [vp, u32]),
+    "kzg_bench_imad_peak": (i32, [vp, u32, C.POINTER(C.c_double)]),
+    "kzg_bench_modmul_peak": (i32, [vp, u32, C.POINTER(C.c_double)]),
+    "kzg_ctx_kernel_time": (i32, [vp, u32, i32, C.POINTER(C.c_double), C.POINTER(u64)]),
     "kzg_srs_load_ptau": (i32, [vp, C.c_char_p, u64, C.POINTER(vp), C.POINTER(u32)]),
     "kzg_ptau_read_header": (i32, [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32)]),
     "kzg_ptau_read_tau_g2": (i32, [vp, C.c_char_p, vp]),
     "kzg_srs_from_host": (i32, [vp, vp, u64, C.POINTER(vp)]),
     "kzg_srs_generate": (i32, [vp, vp, u64, C.POINTER(vp)]),
+    "kzg_srs_generate_range": (i32, [vp, vp, u64, u64, C.POINTER(vp)]),
     "kzg_srs_write_ptau": (i32, [vp, vp, u32, vp, vp, C.c_char_p]),
     "kzg_srs_download": (i32, [vp, vp, u64, u64, vp]),
     "kzg_srs_len": (u64, [vp]),
+    "kzg_srs_device_ptr": (vp, [vp]),
     "kzg_srs_free": (i32, [vp, vp]),
     "kzg_buf_alloc": (i32, [vp, u64, C.POINTER(vp)]),
     "kzg_buf_free": (i32, [vp, vp]),
@@ -66,6 +71,7 @@ SIGNATURES = {
     "kzg_srs_msm": (i32, [vp, vp, u64, vp, u64, vp]),
     "kzg_srs_msm_partial": (i32, [vp, vp, u64, vp, u64, vp]),
     "kzg_g1_partials_combine": (i32, [vp, vp, u32, vp]),
+    "kzg_msm_geometry": (i32, [vp, u64, i32, C.POINTER(u32), C.POINTER(u32)]),
     "kzg_msm_set_window": (i32, [vp, u32]),
     "kzg_prover_create": (i32, [vp, vp, i32, u32, u32, i32, C.POINTER(vp)]),
     "kzg_prover_destroy": (i32, [vp]),

@@ -17,6 +17,10 @@ struct kzg_ctx {
     std::string err;
     uint64_t launches = 0;
     uint32_t msm_window = 0;  // 0 = auto
+    // optional per-kernel device timing (bench.py's live roofline): event pairs around tagged launches
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];
+    std::vector<cudaEvent_t> event_pool;
     // twiddle tables (device): W = w_{2^26}; lo[i] = W^i, hi[j] = W^(j * 8192); [0] forward, [1] inverse
     kzg::Fr* tw_lo[2] = {nullptr, nullptr};
     kzg::Fr* tw_hi[2] = {nullptr, nullptr};
@@ -74,6 +78,11 @@ int set_err(kzg_ctx* ctx, int code, const std::string& msg);
     } while (0)
 
 #define KZG_CHECK_LAUNCH(ctx) KZG_CUDA(ctx, cudaGetLastError())
+
+// tags for kzg_ctx_kernel_time
+enum { KZG_TIMED_MSM_ACCUMULATE = 0, KZG_TIMED_NTT = 1 };
+void timed_begin(kzg_ctx* ctx, int tag);
+void timed_end(kzg_ctx* ctx, int tag);
 
 int ctx_scratch(kzg_ctx* ctx, size_t bytes, void** out);
 int buf_new(kzg_ctx* ctx, uint64_t n, bool zero, kzg_buf** out);

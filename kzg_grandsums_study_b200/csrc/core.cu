@@ -10,6 +10,75 @@ int set_err(kzg_ctx* ctx, int code, const std::string& msg) {
     return code;
 }
 
+static cudaEvent_t take_event(kzg_ctx* ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void timed_begin(kzg_ctx* ctx, int tag) {
+    if (!ctx->timing) return;
+    cudaEvent_t a = take_event(ctx), b = take_event(ctx);
+    cudaEventRecord(a, ctx->stream);
+    ctx->timed[tag].push_back({a, b});
+}
+void timed_end(kzg_ctx* ctx, int tag) {
+    if (!ctx->timing || ctx->timed[tag].empty()) return;
+    cudaEventRecord(ctx->timed[tag].back().second, ctx->stream);
+}
+
+// four independent carry chains of wide multiply-accumulates per thread (the cmad4 building block of fp_mul:
+// each mad.lo.cc / madc.hi.cc pair is one IMAD.WIDE.U32[.X] in SASS); 16 MACs per inner step
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t iters, uint32_t seed, unsigned long long* sink) {
+#if defined(__CUDA_ARCH__)
+    uint32_t x[8], y = (seed ^ 0x9e3779b9u) + blockIdx.x * 40503u + threadIdx.x;
+    uint32_t a0[8], a1[8], a2[8], a3[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        x[k] = seed * (2 * k + 1) + threadIdx.x * 2654435761u;
+        a0[k] = a1[k] = a2[k] = a3[k] = k;
+    }
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            cmad4(a0, x[0], x[2], x[4], x[6], y);
+            cmad4(a1, x[1], x[3], x[5], x[7], y);
+            cmad4(a2, x[0], x[3], x[4], x[7], y);
+            cmad4(a3, x[1], x[2], x[5], x[6], y);
+            y += 0x9e3779b9u;
+        }
+    }
+    unsigned long long z = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) z ^= a0[k] ^ a1[k] ^ a2[k] ^ a3[k];
+    if (z == 0x1234567ull) *sink = z;  // keeps the chains live
+#endif
+}
+
+// the practical ceiling of the field kernels: back-to-back Montgomery products held in registers
+// (two independent chains per thread), counted as 136 limb-MACs each
+__global__ void __launch_bounds__(256) modmul_peak_kernel(uint32_t iters, uint32_t seed, uint32_t* sink) {
+    Fq x = fp_one<FqP>(), y = fp_r2<FqP>();
+    x.l[0] += (seed + threadIdx.x) & 0xffff;
+    y.l[0] ^= (blockIdx.x * 7u + seed) & 0xffff;
+    Fq u = y, w = x;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            x = fp_mul(x, y);
+            u = fp_mul(u, w);
+        }
+    }
+    uint32_t z = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) z ^= x.l[k] ^ u.l[k];
+    if (z == 0x1234567u) *sink = z;
+}
+
 int ctx_scratch(kzg_ctx* ctx, size_t bytes, void** out) {
     if (bytes > ctx->scratch_bytes) {
         // stream-ordered free of the old block, then a fresh (larger) one; rounded up to limit regrowth
@@ -191,6 +260,12 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
         cudaFree(ctx->tw_lo[d]);
         cudaFree(ctx->tw_hi[d]);
     }
+    for (int tag = 0; tag < 2; tag++)
+        for (auto& pr : ctx->timed[tag]) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     cudaFree(ctx->scratch);
     cudaFree(ctx->dev_small);
     cudaFreeHost(ctx->pinned);
@@ -219,6 +294,73 @@ int kzg_selftest(kzg_ctx* ctx, uint32_t n_cases) {
     unsigned int fails;
     memcpy(&fails, ctx->pinned, sizeof(fails));
     if (fails) return set_err(ctx, KZG_ERR_CUDA, "device self-test failed in " + std::to_string(fails) + " cases");
+    return KZG_OK;
+}
+
+// which = 0: raw IMAD.WIDE.U32 chains; which = 1: fp_mul chains (reported as 136 MACs per product)
+static int bench_peak(kzg_ctx* ctx, int which, uint32_t ms, double* macs_per_second) {
+    cudaEvent_t a, b;
+    KZG_CUDA(ctx, cudaEventCreate(&a));
+    KZG_CUDA(ctx, cudaEventCreate(&b));
+    const uint32_t blocks = (uint32_t)ctx->sm_count * 8, threads = 256;
+    void* sink = (void*)(ctx->dev_small + 2048);
+    uint32_t iters = which == 0 ? 1024 : 64;
+    const double macs_per_iter = which == 0 ? 64.0 : 8.0 * 136.0;
+    double best = 0;
+    float total_ms = 0;
+    // warm up, then repeat launches until `ms` of kernel time has been spent; report the best launch
+    for (int rep = 0; rep < 64 && (rep < 3 || total_ms < (float)ms); rep++) {
+        KZG_CUDA(ctx, cudaEventRecord(a, ctx->stream));
+        if (which == 0)
+            KZG_LAUNCH(ctx, imad_peak_kernel, blocks, threads, 0, iters, 12345u + rep, (unsigned long long*)sink);
+        else
+            KZG_LAUNCH(ctx, modmul_peak_kernel, blocks, threads, 0, iters, 12345u + rep, (uint32_t*)sink);
+        KZG_CUDA(ctx, cudaEventRecord(b, ctx->stream));
+        KZG_CUDA(ctx, cudaEventSynchronize(b));
+        float t = 0;
+        KZG_CUDA(ctx, cudaEventElapsedTime(&t, a, b));
+        if (rep >= 1) {
+            total_ms += t;
+            double rate = (double)blocks * threads * (double)iters * macs_per_iter / (t * 1e-3);
+            if (rate > best) best = rate;
+        }
+        if (t < 2.0f && iters < (1u << 22)) iters *= 4;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *macs_per_second = best;
+    return KZG_OK;
+}
+
+int kzg_bench_imad_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second) {
+    if (!ctx || !macs_per_second) return KZG_ERR_ARG;
+    return bench_peak(ctx, 0, ms, macs_per_second);
+}
+int kzg_bench_modmul_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second) {
+    if (!ctx || !macs_per_second) return KZG_ERR_ARG;
+    return bench_peak(ctx, 1, ms, macs_per_second);
+}
+
+int kzg_ctx_kernel_time(kzg_ctx* ctx, uint32_t which, int reset, double* ms_out, uint64_t* launches_out) {
+    if (!ctx || which > 1) return KZG_ERR_ARG;
+    KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double total = 0;
+    for (auto& pr : ctx->timed[which]) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) total += t;
+    }
+    if (ms_out) *ms_out = total;
+    if (launches_out) *launches_out = ctx->timed[which].size();
+    if (reset) {
+        for (int tag = 0; tag < 2; tag++) {
+            for (auto& pr : ctx->timed[tag]) {
+                ctx->event_pool.push_back(pr.first);
+                ctx->event_pool.push_back(pr.second);
+            }
+            ctx->timed[tag].clear();
+        }
+        ctx->timing = reset > 0;  // reset = 1: clear and (keep) timing on; reset = -1: clear and switch off
+    }
     return KZG_OK;
 }
 

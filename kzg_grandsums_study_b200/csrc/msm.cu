@@ -77,48 +77,121 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------
 // scan of bucket sizes: offsets[k] = sum_{j<k} counts[j], segoff[k] = sum_{j<k} ceil(counts[j]/seg)
-// (single block; K <= ~10^7 keys, a few tens of microseconds)
+// Three phases over tiles of SCAN_TILE keys: tile sums, one-block scan of the tile sums, apply.
+// Buckets that need more than one accumulate task are appended to `heavy` (collapsed after accumulation).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t nkeys, uint32_t seg,
-                                                        uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
-                                                        uint32_t* __restrict__ segoff) {
-    __shared__ uint32_t sh_a[1024];
-    __shared__ uint32_t sh_b[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t per = (nkeys + 1023) / 1024;
-    const uint32_t lo = min(tid * per, nkeys), hi = min(lo + per, nkeys);
-    uint32_t sa = 0, sb = 0;
-    for (uint32_t k = lo; k < hi; k++) {
-        uint32_t cnt = counts[k];
-        sa += cnt;
-        sb += (cnt + seg - 1) / seg;
-    }
-    sh_a[tid] = sa;
-    sh_b[tid] = sb;
-    __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {
-        uint32_t va = 0, vb = 0;
-        if (tid >= d) {
-            va = sh_a[tid - d];
-            vb = sh_b[tid - d];
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ uint2 block_scan_pair(uint2 v, uint2* sh, uint2& total) {
+    // inclusive scan of (a, b) pairs across the block
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        uint32_t oa = __shfl_up_sync(0xffffffffu, v.x, d), ob = __shfl_up_sync(0xffffffffu, v.y, d);
+        if (lane >= d) {
+            v.x += oa;
+            v.y += ob;
         }
+    }
+    if (lane == 31) sh[wid] = v;
+    __syncthreads();
+    uint2 carry = make_uint2(0, 0), tot = make_uint2(0, 0);
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+        uint2 x = sh[w];
+        if (w < (int)wid) {
+            carry.x += x.x;
+            carry.y += x.y;
+        }
+        tot.x += x.x;
+        tot.y += x.y;
+    }
+    __syncthreads();
+    total = tot;
+    return make_uint2(v.x + carry.x, v.y + carry.y);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t nkeys,
+                                                                      uint32_t seg, uint2* __restrict__ tile_sums) {
+    __shared__ uint2 sh[SCAN_THREADS / 32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x;
+    uint2 acc = make_uint2(0, 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        uint32_t i = base + k * SCAN_THREADS;
+        if (i < nkeys) {
+            uint32_t cnt = counts[i];
+            acc.x += cnt;
+            acc.y += (cnt + seg - 1) / seg;
+        }
+    }
+    uint2 tot;
+    block_scan_pair(acc, sh, tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of the tile sums in place; totals -> offsets[nkeys], segoff[nkeys]
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_sums_kernel(uint2* __restrict__ tile_sums, uint32_t ntiles,
+                                                                     uint32_t nkeys, uint32_t* __restrict__ offsets,
+                                                                     uint32_t* __restrict__ segoff) {
+    __shared__ uint2 sh[SCAN_THREADS / 32];
+    __shared__ uint2 carry_sh;
+    if (threadIdx.x == 0) carry_sh = make_uint2(0, 0);
+    __syncthreads();
+    for (uint32_t start = 0; start < ntiles; start += SCAN_THREADS) {
+        uint32_t i = start + threadIdx.x;
+        uint2 v = i < ntiles ? tile_sums[i] : make_uint2(0, 0);
+        uint2 tot;
+        uint2 inc = block_scan_pair(v, sh, tot);
+        uint2 c = carry_sh;
+        if (i < ntiles) tile_sums[i] = make_uint2(c.x + inc.x - v.x, c.y + inc.y - v.y);
         __syncthreads();
-        sh_a[tid] += va;
-        sh_b[tid] += vb;
+        if (threadIdx.x == 0) carry_sh = make_uint2(c.x + tot.x, c.y + tot.y);
         __syncthreads();
     }
-    uint32_t ra = sh_a[tid] - sa, rb = sh_b[tid] - sb;  // exclusive
-    for (uint32_t k = lo; k < hi; k++) {
-        uint32_t cnt = counts[k];
-        offsets[k] = ra;
-        cursor[k] = ra;
-        segoff[k] = rb;
-        ra += cnt;
-        rb += (cnt + seg - 1) / seg;
+    if (threadIdx.x == 0) {
+        offsets[nkeys] = carry_sh.x;
+        segoff[nkeys] = carry_sh.y;
     }
-    if (tid == 1023) {
-        offsets[nkeys] = sh_a[1023];
-        segoff[nkeys] = sh_b[1023];
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(const uint32_t* __restrict__ counts, uint32_t nkeys,
+                                                                      uint32_t seg, const uint2* __restrict__ tile_sums,
+                                                                      uint32_t* __restrict__ offsets,
+                                                                      uint32_t* __restrict__ cursor,
+                                                                      uint32_t* __restrict__ segoff,
+                                                                      uint32_t* __restrict__ heavy,
+                                                                      uint32_t* __restrict__ heavy_count) {
+    __shared__ uint2 sh[SCAN_THREADS / 32];
+    // thread owns SCAN_PER_THREAD consecutive keys so that its partial results are a running sum
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t cnt[SCAN_PER_THREAD];
+    uint2 acc = make_uint2(0, 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        uint32_t i = base + k;
+        cnt[k] = i < nkeys ? counts[i] : 0;
+        acc.x += cnt[k];
+        acc.y += (cnt[k] + seg - 1) / seg;
+    }
+    uint2 tot;
+    uint2 inc = block_scan_pair(acc, sh, tot);
+    uint2 t0 = tile_sums[blockIdx.x];
+    uint32_t ra = t0.x + inc.x - acc.x, rb = t0.y + inc.y - acc.y;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        uint32_t i = base + k;
+        if (i < nkeys) {
+            offsets[i] = ra;
+            cursor[i] = ra;
+            segoff[i] = rb;
+            uint32_t nseg = (cnt[k] + seg - 1) / seg;
+            if (nseg > 1) heavy[atomicAdd(heavy_count, 1u)] = i;
+            ra += cnt[k];
+            rb += nseg;
+        }
     }
 }
 
@@ -188,16 +261,44 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
     store_xyzz(partials + t, acc);
 }
 
-// sum of the segment partials of one bucket (usually exactly one)
+// After accumulation a bucket that was split over several tasks holds several partial sums: one block per
+// such bucket tree-sums them in shared memory and leaves the total in the bucket's first slot.
+constexpr int COLLAPSE_THREADS = 128;
+__global__ void __launch_bounds__(COLLAPSE_THREADS) msm_collapse_kernel(G1XYZZ* __restrict__ partials,
+                                                                        const uint32_t* __restrict__ segoff,
+                                                                        const uint32_t* __restrict__ heavy,
+                                                                        const uint32_t* __restrict__ heavy_count) {
+    __shared__ G1XYZZ sh[COLLAPSE_THREADS];
+    const uint32_t nheavy = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const uint32_t key = heavy[h];
+        const uint32_t a = segoff[key], b = segoff[key + 1];
+        G1XYZZ v = xyzz_inf();
+        for (uint32_t j = a + threadIdx.x; j < b; j += COLLAPSE_THREADS) {
+            G1XYZZ o = load_xyzz(partials + j);
+            xyzz_add(v, o);
+        }
+        store_xyzz(sh + threadIdx.x, v);
+        __syncthreads();
+        for (uint32_t s = COLLAPSE_THREADS / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                G1XYZZ x = load_xyzz(sh + threadIdx.x);
+                G1XYZZ y = load_xyzz(sh + threadIdx.x + s);
+                xyzz_add(x, y);
+                store_xyzz(sh + threadIdx.x, x);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_xyzz(partials + a, load_xyzz(sh));
+        __syncthreads();
+    }
+}
+
+// the (collapsed) sum of one bucket
 __device__ __forceinline__ G1XYZZ load_bucket(const G1XYZZ* partials, const uint32_t* segoff, uint32_t key) {
     uint32_t a = segoff[key], b = segoff[key + 1];
     if (a == b) return xyzz_inf();
-    G1XYZZ v = load_xyzz(partials + a);
-    for (uint32_t j = a + 1; j < b; j++) {
-        G1XYZZ o = load_xyzz(partials + j);
-        xyzz_add(v, o);
-    }
-    return v;
+    return load_xyzz(partials + a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -302,21 +403,27 @@ static uint32_t auto_window(uint64_t n) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev) {
-    if (n == 0) {
-        KZG_CUDA(ctx, cudaMemsetAsync(result_dev, 0, sizeof(G1XYZZ), ctx->stream));
-        return KZG_OK;
-    }
-    if (n >= (1ull << 27)) return set_err(ctx, KZG_ERR_ARG, "msm: at most 2^27 - 1 points per call");
+static MsmGeom msm_geometry(kzg_ctx* ctx, uint64_t n, bool montgomery) {
     MsmGeom g;
     g.c = ctx->msm_window ? ctx->msm_window : auto_window(n);
     if (g.c < 2) g.c = 2;
     if (g.c > 22) g.c = 22;
     // Montgomery sources are reduced (< r < 2^254): ceil(255/c) windows leave the top digit carry-free.
     // Raw standard-form scalars may use all 256 bits: ceil(257/c).
-    const uint32_t bits = src.montgomery ? 255 : 257;
+    const uint32_t bits = montgomery ? 255 : 257;
     g.nwin = (bits + g.c - 1) / g.c;
     g.nbuckets = 1u << (g.c - 1);
+    g.seg = 0;
+    return g;
+}
+
+int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev) {
+    if (n == 0) {
+        KZG_CUDA(ctx, cudaMemsetAsync(result_dev, 0, sizeof(G1XYZZ), ctx->stream));
+        return KZG_OK;
+    }
+    if (n >= (1ull << 27)) return set_err(ctx, KZG_ERR_ARG, "msm: at most 2^27 - 1 points per call");
+    MsmGeom g = msm_geometry(ctx, n, src.montgomery);
     const uint64_t avg = n / g.nbuckets + 1;
     uint64_t seg = 4 * avg;
     if (seg < 256) seg = 256;
@@ -340,6 +447,9 @@ int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G
     const size_t o_partials = off; off = align_up(off + sizeof(G1XYZZ) * max_tasks, 256);
     const size_t o_red = off;      off = align_up(off + sizeof(G1XYZZ) * (size_t)g.nwin * red_blocks, 256);
     const size_t o_windows = off;  off = align_up(off + sizeof(G1XYZZ) * g.nwin, 256);
+    const uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
+    const size_t o_tiles = off;    off = align_up(off + sizeof(uint2) * ntiles, 256);
+    const size_t o_heavy = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     void* base = nullptr;
     KZG_TRY(ctx_scratch(ctx, off, &base));
     uint8_t* sc = (uint8_t*)base;
@@ -351,14 +461,23 @@ int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G
     G1XYZZ* partials = (G1XYZZ*)(sc + o_partials);
     G1XYZZ* red = (G1XYZZ*)(sc + o_red);
     G1XYZZ* windows = (G1XYZZ*)(sc + o_windows);
+    uint2* tile_sums = (uint2*)(sc + o_tiles);
+    uint32_t* heavy = (uint32_t*)(sc + o_heavy);       // [0] = count, [1..] = keys
 
     KZG_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nkeys + 1), ctx->stream));
+    KZG_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), ctx->stream));
     const uint32_t dblocks = (uint32_t)((n + 255) / 256);
     KZG_LAUNCH(ctx, msm_digits_kernel<false>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, counts, nullptr);
-    KZG_LAUNCH(ctx, msm_scan_kernel, 1, 1024, 0, counts, nkeys, g.seg, offsets, cursor, segoff);
+    KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, nkeys, g.seg, tile_sums);
+    KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, offsets, segoff);
+    KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, nkeys, g.seg, tile_sums, offsets, cursor, segoff,
+               heavy + 1, heavy);
     KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
     const uint32_t ablocks = (uint32_t)((max_tasks + 127) / 128);
+    timed_begin(ctx, KZG_TIMED_MSM_ACCUMULATE);
     KZG_LAUNCH(ctx, msm_accumulate_kernel, ablocks, 128, 0, bases, sorted, offsets, segoff, nkeys, g.seg, partials);
+    timed_end(ctx, KZG_TIMED_MSM_ACCUMULATE);
+    KZG_LAUNCH(ctx, msm_collapse_kernel, (uint32_t)ctx->sm_count * 2, COLLAPSE_THREADS, 0, partials, segoff, heavy + 1, heavy);
     KZG_LAUNCH(ctx, msm_reduce1_kernel, dim3(red_blocks, g.nwin), RED_THREADS, 0, partials, segoff, g, red_chunk, red);
     KZG_LAUNCH(ctx, msm_reduce2_kernel, g.nwin, RED_THREADS, 0, red, red_blocks, windows);
     KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, windows, g, result_dev);
@@ -385,6 +504,14 @@ using namespace kzg;
 static inline G1XYZZ* result_slot(kzg_ctx* ctx) { return (G1XYZZ*)(ctx->dev_small + 1024); }
 
 extern "C" {
+
+int kzg_msm_geometry(kzg_ctx* ctx, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows) {
+    if (!ctx) return KZG_ERR_ARG;
+    MsmGeom g = msm_geometry(ctx, n ? n : 1, montgomery != 0);
+    if (window_bits) *window_bits = g.c;
+    if (windows) *windows = g.nwin;
+    return KZG_OK;
+}
 
 int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c) {
     if (!ctx) return KZG_ERR_ARG;

@@ -194,11 +194,15 @@ int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs
 }
 
 int kzg_srs_generate(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t n_points, kzg_srs** out) {
+    return kzg_srs_generate_range(ctx, tau_std, 0, n_points, out);
+}
+
+int kzg_srs_generate_range(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t first, uint64_t n_points, kzg_srs** out) {
     if (!ctx || !tau_std || !out) return KZG_ERR_ARG;
     kzg_srs* s = new kzg_srs();
     s->n = n_points;
     uint32_t power = 0;
-    while ((2ull << power) < n_points) power++;  // a power-p file holds ~2^(p+1) points
+    while ((2ull << power) < first + n_points) power++;  // a power-p file holds ~2^(p+1) points
     s->power = power;
     if (n_points == 0) {
         *out = s;
@@ -218,7 +222,7 @@ int kzg_srs_generate(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t n_points,
     }
     Fr tau = fp_to_mont(fr_from_bytes(tau_std));
     KZG_LAUNCH(ctx, srs_table_kernel, 1, 32, 0, table);
-    KZG_LAUNCH(ctx, srs_points_kernel, (uint32_t)((n_points + 127) / 128), 128, 0, table, tau, (uint64_t)0, n_points, s->d);
+    KZG_LAUNCH(ctx, srs_points_kernel, (uint32_t)((n_points + 127) / 128), 128, 0, table, tau, first, n_points, s->d);
     e = cudaGetLastError();
     cudaFreeAsync(table, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -272,6 +276,7 @@ int kzg_srs_write_ptau(kzg_ctx* ctx, kzg_srs* srs, uint32_t power, const uint8_t
 }
 
 uint64_t kzg_srs_len(kzg_srs* srs) { return srs ? srs->n : 0; }
+void* kzg_srs_device_ptr(kzg_srs* srs) { return srs ? (void*)srs->d : nullptr; }
 
 int kzg_srs_free(kzg_ctx* ctx, kzg_srs* srs) {
     if (!srs) return KZG_OK;
