@@ -147,9 +147,17 @@ int kzg_srs_msm(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std
  * partials, kzg_g1_partials_combine adds `count` of them and returns the affine point. */
 int kzg_srs_msm_partial(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std, uint64_t n, void* partial_dev);
 int kzg_g1_partials_combine(kzg_ctx* ctx, const void* partials_dev, uint32_t count, uint8_t out_affine[64]);
-/* MSM tuning: window bits (0 = auto from n); kzg_msm_geometry reports what an n-point MSM will use
- * (montgomery = 1 for kzg_commit's scalars, 0 for standard-form scalars) */
-int kzg_msm_geometry(kzg_ctx* ctx, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows);
+/* Same, scalars in HOST memory (H2D inside the call): the end-to-end form of kzg_srs_msm. */
+int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
+                     uint8_t out_affine[64]);
+/* One-off per resident SRS: the window table T[w][i] = 2^(c w) [tau^i]_1 that lets every MSM over this SRS use a
+ * single shared bucket set (fewer, larger windows; no doubling chain).  window_bits = 0 picks c from the SRS size.
+ * Costs ceil(257/c) x the SRS memory.  Without it the SRS entry points fall back to the per-window MSM. */
+int kzg_srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t window_bits);
+/* MSM tuning for the per-window (table-less) path: window bits (0 = auto from n); a non-zero value also makes
+ * the SRS entry points ignore their table.  kzg_msm_geometry reports what an n-point MSM will use (srs may be
+ * NULL for the raw kzg_g1_msm_affine path; montgomery = 1 for kzg_commit's scalars, 0 for standard form). */
+int kzg_msm_geometry(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows);
 int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c);
 
 /* ---- fused provers (prover.js:144-413 and the grand-product twin) --------------------------------------- */

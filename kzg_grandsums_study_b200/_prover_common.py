@@ -37,20 +37,25 @@ def prove(kind, pTauFilename, evalsFs, evalsTs, evalsSelF=None, evalsSelT=None, 
             raise ValueError("The %d-th multiset buffers must have the same length." % i)
         if evalsFs[i].length() != evalsFs[0].length():
             raise ValueError("The multiset buffers must all have the same length.")
-    if evalsSelF is None:                                       # :48-53
-        evalsSelF = Evaluations.getOneEvals(evalsFs[0].length(), curve)
-    if evalsSelT is None:
-        evalsSelT = Evaluations.getOneEvals(evalsTs[0].length(), curve)
-    if evalsSelF.length() != evalsSelT.length():                # :56-60
-        raise ValueError("The selection buffers must have the same length.")
-    if evalsSelF.length() != evalsFs[0].length():
-        raise ValueError("The selection buffers must have the same length as the multiset buffers.")
-    isSelected = True                                           # :63-68
-    if evalsSelF.isAllOnes() and evalsSelT.isAllOnes():
+    # :48-68.  Selectors that are not provided mean "all ones"; the reference materialises them and then finds
+    # out they are all ones -- the outcome (isSelected = false) is known without building 2 x 32n bytes.
+    if evalsSelF is None and evalsSelT is None:
         isSelected = False
-    elif evalsSelF.isAllZeros() and evalsSelT.isAllZeros():
-        if logger:
-            logger.warning("The selection buffers are all zeros. The argument is trivially satisfied.")
+    else:
+        if evalsSelF is None:
+            evalsSelF = Evaluations.getOneEvals(evalsFs[0].length(), curve)
+        if evalsSelT is None:
+            evalsSelT = Evaluations.getOneEvals(evalsTs[0].length(), curve)
+        if evalsSelF.length() != evalsSelT.length():            # :56-60
+            raise ValueError("The selection buffers must have the same length.")
+        if evalsSelF.length() != evalsFs[0].length():
+            raise ValueError("The selection buffers must have the same length as the multiset buffers.")
+        isSelected = True                                       # :63-68
+        if evalsSelF.isAllOnes() and evalsSelT.isAllOnes():
+            isSelected = False
+        elif evalsSelF.isAllZeros() and evalsSelT.isAllZeros():
+            if logger:
+                logger.warning("The selection buffers are all zeros. The argument is trivially satisfied.")
     length = evalsFs[0].length()
     nBits = math.ceil(math.log2(length)) if length > 0 else 0   # :70-71
     domainSize = 2 ** nBits

@@ -45,6 +45,9 @@ struct kzg_srs {
     kzg::G1Affine* d = nullptr;
     uint64_t n = 0;
     uint32_t power = 0;
+    // precomputed window table T[w][i] = 2^(tab_c * w) * P_i, w < tab_nwin, row stride n (msm.cu); optional
+    kzg::G1Affine* table = nullptr;
+    uint32_t tab_c = 0, tab_nwin = 0;
 };
 
 namespace kzg {
@@ -96,7 +99,15 @@ struct MsmScalarSrc {
     const Fr* scalars;  // device
     bool montgomery;    // true: convert from Montgomery on the fly (commit of a polynomial)
 };
-int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev);
+struct MsmBases {
+    const G1Affine* pts;    // plain points (raw flavour)
+    const G1Affine* table;  // window table, already offset to the first point of the slice (nullptr: raw flavour)
+    uint64_t stride;        // table row stride in points
+    uint32_t tab_c, tab_nwin;
+};
+int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev);
+MsmBases srs_bases(kzg_ctx* ctx, const kzg_srs* srs, uint64_t first);
+int srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t c);
 int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t count, uint8_t out[64]);
 // frops.cu
 int fr_convert(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n, bool to_mont);

@@ -1,21 +1,31 @@
 // Signed-digit Pippenger G1 MSM for sm_100a.   Replaces G1.multiExpAffine + G1.toAffine
 // (reference src/polynomial/polynomial.js:1106-1115, the un-vendored ffjavascript/wasmcurves call).
 //
-// Pipeline (all on one stream, no host round trip until the 64-byte result is read):
-//   1. msm_count      : scalars -> signed c-bit digits (optionally leaving Montgomery form first,
-//                       Fr.batchFromMontgomery fused), histogram of bucket keys (L2 atomics).
-//   2. msm_scan       : exclusive prefix sums of bucket sizes and of per-bucket segment counts.
-//   3. msm_scatter    : counting-sort scatter of (point index | sign) into bucket order.
-//   4. msm_accumulate : one thread per bucket segment, XYZZ += affine over its slice of the sorted
-//                       list (random 64 B gathers from the resident SRS, next point prefetched while the
-//                       current one is being added).  This is the IMAD-bound kernel: 10 modmul per entry.
-//   5. msm_reduce_1/2 : weighted bucket sums  sum_b (b+1) * S_b  per window: chunked running sums,
-//                       shared-memory tree over the chunk partials.
-//   6. msm_horner     : combine the windows (c doublings each) -> one XYZZ point in device memory.
-//   7. g1_finish      : sum `count` partial points (count > 1 only for the multi-GPU gather) and convert
-//                       to the canonical affine encoding.
-// The result is a canonical group element, so it is byte-identical to the reference's regardless of
-// window size, digit signedness or summation order.
+// Two flavours share one pipeline:
+//   * SRS MSM (commit, kzg_srs_msm): the SRS carries a precomputed table T[w][i] = 2^(c w) * P_i (affine),
+//     built once when the SRS is made resident.  Every (point, window) digit then lands in ONE shared set of
+//     2^(c-1) buckets, so there is a single bucket reduction and no doubling chain at the end, and c can be
+//     large (22 bits at 2^24 points -> 12 digits per scalar instead of 16).  180 GB of HBM pay for it:
+//     12 x 1 GiB at 2^24 points.
+//   * raw MSM (kzg_g1_msm_affine on caller-supplied bases): classic per-window bucket sets, windows combined
+//     by a Horner chain of doublings.
+//
+// Pipeline (one stream, no host round trip until the 64-byte result is read):
+//   1. msm_digits<count>  scalars -> signed c-bit digits (leaving Montgomery form first when the source is a
+//                         polynomial: Fr.batchFromMontgomery fused), histogram of bucket keys (L2 atomics)
+//   2. msm_scan_*         exclusive prefix sums of bucket sizes and of per-bucket task counts (3 small launches)
+//   3. msm_digits<scatter> counting-sort scatter of (point index | sign) into bucket order
+//   4. msm_accumulate     one thread per task (a bucket, or a slice of an overfull one): XYZZ += affine over its
+//                         slice of the sorted list; random 64 B gathers, next point prefetched during the add.
+//                         THE IMAD-bound kernel: 10 modmul (1360 limb MACs) per entry.
+//   5. msm_collapse       buckets that were split over several tasks: block-parallel sum of their partials
+//   6. msm_reduce_level   sum_b (b+1) S_b by a radix-16 hierarchy: each level folds 16 consecutive buckets into a
+//                         weighted partial (running-sum trick) and a plain sum that feeds the next level
+//   7. msm_reduce_final   Horner over the levels (4 doublings each) -> one XYZZ per bucket set
+//   8. msm_horner         raw flavour only: combine the windows (c doublings each)
+//   9. g1_finish          sum `count` partial points (count > 1 only for the multi-GPU gather), canonical affine
+// The result is a canonical group element, so it is byte-identical to the reference's regardless of window
+// size, digit signedness, precomputation or summation order.
 #include <string.h>
 
 #include "common.cuh"
@@ -23,13 +33,15 @@
 namespace kzg {
 
 // ---------------------------------------------------------------------------------------------
-// digits
+// geometry
 // ---------------------------------------------------------------------------------------------
 struct MsmGeom {
-    uint32_t c;        // window bits
-    uint32_t nwin;     // number of windows
-    uint32_t nbuckets; // buckets per window = 2^(c-1)
-    uint32_t seg;      // max entries per accumulate task
+    uint32_t c;         // window bits
+    uint32_t nwin;      // digits per scalar
+    uint32_t nbuckets;  // buckets per set = 2^(c-1)
+    uint32_t nsets;     // bucket sets: 1 with a precomputed table, nwin without
+    uint32_t seg;       // max entries per accumulate task
+    uint64_t stride;    // table flavour: entry = w * stride + i
 };
 
 __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, uint32_t pos, uint32_t c) {
@@ -51,6 +63,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
     if (montgomery) s = fp_from_mont(s);
     uint32_t carry = 0;
     const uint32_t half = g.nbuckets;  // 2^(c-1)
+    const bool table = g.nsets == 1;
     for (uint32_t w = 0; w < g.nwin; w++) {
         uint32_t raw = scalar_bits(s.l, w * g.c, g.c) + carry;
         uint32_t mag, neg;
@@ -64,10 +77,11 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
             carry = 0;
         }
         if (mag != 0) {
-            uint32_t key = w * g.nbuckets + (mag - 1);
+            uint32_t key = (table ? 0u : w * g.nbuckets) + (mag - 1);
             if (SCATTER) {
                 uint32_t pos = atomicAdd(&counts_or_cursor[key], 1u);
-                sorted[pos] = (uint32_t)i | (neg << 31);
+                uint32_t entry = table ? (uint32_t)(w * g.stride + i) : (uint32_t)i;
+                sorted[pos] = entry | (neg << 31);
             } else {
                 atomicAdd(&counts_or_cursor[key], 1u);
             }
@@ -263,47 +277,6 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
 
 // After accumulation a bucket that was split over several tasks holds several partial sums: one block per
 // such bucket tree-sums them in shared memory and leaves the total in the bucket's first slot.
-constexpr int COLLAPSE_THREADS = 128;
-__global__ void __launch_bounds__(COLLAPSE_THREADS) msm_collapse_kernel(G1XYZZ* __restrict__ partials,
-                                                                        const uint32_t* __restrict__ segoff,
-                                                                        const uint32_t* __restrict__ heavy,
-                                                                        const uint32_t* __restrict__ heavy_count) {
-    __shared__ G1XYZZ sh[COLLAPSE_THREADS];
-    const uint32_t nheavy = *heavy_count;
-    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
-        const uint32_t key = heavy[h];
-        const uint32_t a = segoff[key], b = segoff[key + 1];
-        G1XYZZ v = xyzz_inf();
-        for (uint32_t j = a + threadIdx.x; j < b; j += COLLAPSE_THREADS) {
-            G1XYZZ o = load_xyzz(partials + j);
-            xyzz_add(v, o);
-        }
-        store_xyzz(sh + threadIdx.x, v);
-        __syncthreads();
-        for (uint32_t s = COLLAPSE_THREADS / 2; s > 0; s >>= 1) {
-            if (threadIdx.x < s) {
-                G1XYZZ x = load_xyzz(sh + threadIdx.x);
-                G1XYZZ y = load_xyzz(sh + threadIdx.x + s);
-                xyzz_add(x, y);
-                store_xyzz(sh + threadIdx.x, x);
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) store_xyzz(partials + a, load_xyzz(sh));
-        __syncthreads();
-    }
-}
-
-// the (collapsed) sum of one bucket
-__device__ __forceinline__ G1XYZZ load_bucket(const G1XYZZ* partials, const uint32_t* segoff, uint32_t key) {
-    uint32_t a = segoff[key], b = segoff[key + 1];
-    if (a == b) return xyzz_inf();
-    return load_xyzz(partials + a);
-}
-
-// ---------------------------------------------------------------------------------------------
-// bucket reduction: per window  sum_{b<B} (b+1) * S_b
-// ---------------------------------------------------------------------------------------------
 constexpr int RED_THREADS = 128;
 
 __device__ __forceinline__ void block_tree_sum(G1XYZZ& v, G1XYZZ* sh) {
@@ -320,56 +293,106 @@ __device__ __forceinline__ void block_tree_sum(G1XYZZ& v, G1XYZZ* sh) {
         __syncthreads();
     }
     v = load_xyzz(sh);
+    __syncthreads();
 }
 
-// grid = (blocks_per_window, nwin); thread -> chunk of `chunk` consecutive buckets
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce1_kernel(const G1XYZZ* __restrict__ partials,
-                                                                  const uint32_t* __restrict__ segoff, MsmGeom g,
-                                                                  uint32_t chunk, G1XYZZ* __restrict__ out) {
+__global__ void __launch_bounds__(RED_THREADS) msm_collapse_kernel(G1XYZZ* __restrict__ partials,
+                                                                   const uint32_t* __restrict__ segoff,
+                                                                   const uint32_t* __restrict__ heavy,
+                                                                   const uint32_t* __restrict__ heavy_count) {
     __shared__ G1XYZZ sh[RED_THREADS];
-    const uint32_t w = blockIdx.y;
-    const uint32_t ci = blockIdx.x * RED_THREADS + threadIdx.x;
-    const uint32_t nch = (g.nbuckets + chunk - 1) / chunk;
-    G1XYZZ total = xyzz_inf();
-    if (ci < nch) {
-        const uint32_t lo = ci * chunk;
-        const uint32_t hi = min(lo + chunk, g.nbuckets);
+    const uint32_t nheavy = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const uint32_t key = heavy[h];
+        const uint32_t a = segoff[key], b = segoff[key + 1];
+        G1XYZZ v = xyzz_inf();
+        for (uint32_t j = a + threadIdx.x; j < b; j += RED_THREADS) {
+            G1XYZZ o = load_xyzz(partials + j);
+            xyzz_add(v, o);
+        }
+        block_tree_sum(v, sh);
+        if (threadIdx.x == 0) store_xyzz(partials + a, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bucket reduction: per set  sum_{b < B} (b+1) S_b , radix-16 hierarchy.
+// With b = 16 q + r:  (b+1) S_b = (r+1) S_b + 16 q S_b, so one level computes, per chunk q of 16 buckets,
+//   t_q = sum_r (r+1) S_{16q+r}   (running-sum trick; block-summed into `level_partials`)
+//   U_q = sum_r S_{16q+r}         (written out: the next level reduces sum_q q U_q = sum_{b'} (b'+1) U_{b'+1})
+// and  total = T_0 + 16 (T_1 + 16 (T_2 + ...)),  T_L = sum_q t_q at level L.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t RED_CHUNK = 16;
+
+// level 0 reads the (collapsed) accumulate output through segoff; higher levels read a dense array whose
+// element 0 carries weight 0 and is skipped (shift = 1).
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_level_kernel(const G1XYZZ* __restrict__ in,
+                                                                       const uint32_t* __restrict__ segoff,
+                                                                       uint32_t n_in, uint32_t in_stride, uint32_t shift,
+                                                                       G1XYZZ* __restrict__ out_u, uint32_t n_out,
+                                                                       G1XYZZ* __restrict__ level_partials) {
+    __shared__ G1XYZZ sh[RED_THREADS];
+    const uint32_t set = blockIdx.y;
+    const uint32_t q = blockIdx.x * RED_THREADS + threadIdx.x;
+    G1XYZZ tot = xyzz_inf();
+    if (q < n_out) {
+        const uint32_t lo = q * RED_CHUNK;
+        const uint32_t hi = min(lo + RED_CHUNK, n_in);
         G1XYZZ run = xyzz_inf();
         for (uint32_t b = hi; b-- > lo;) {
-            G1XYZZ s = load_bucket(partials, segoff, w * g.nbuckets + b);
+            G1XYZZ s;
+            if (segoff) {
+                const uint32_t key = set * in_stride + b;
+                const uint32_t a = segoff[key];
+                s = a == segoff[key + 1] ? xyzz_inf() : load_xyzz(in + a);
+            } else {
+                s = load_xyzz(in + (size_t)set * in_stride + b + shift);
+            }
             xyzz_add(run, s);
-            xyzz_add(total, run);
+            xyzz_add(tot, run);
         }
-        // total = sum (b - lo + 1) S_b ; add lo * run
-        if (lo != 0) {
-            G1XYZZ scaled = xyzz_mul_small(run, lo);
-            xyzz_add(total, scaled);
-        }
+        store_xyzz(out_u + (size_t)set * n_out + q, run);
     }
-    block_tree_sum(total, sh);
-    if (threadIdx.x == 0) store_xyzz(out + (size_t)w * gridDim.x + blockIdx.x, total);
+    block_tree_sum(tot, sh);
+    if (threadIdx.x == 0) store_xyzz(level_partials + (size_t)set * gridDim.x + blockIdx.x, tot);
 }
 
-// grid = nwin; sums the per-block partials of a window
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce2_kernel(const G1XYZZ* __restrict__ in, uint32_t per_window,
-                                                                  G1XYZZ* __restrict__ windows) {
+struct RedLevels {
+    uint32_t nlevels;
+    uint32_t blocks[8];   // block partials per set at each level
+    uint32_t offset[8];   // start of the level inside level_partials (in units of G1XYZZ, per-set blocks contiguous)
+};
+
+// grid = nsets: Horner over the levels, 4 doublings (x16) per level
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_final_kernel(const G1XYZZ* __restrict__ level_partials,
+                                                                       RedLevels lv, G1XYZZ* __restrict__ set_sums) {
     __shared__ G1XYZZ sh[RED_THREADS];
-    const uint32_t w = blockIdx.x;
-    G1XYZZ total = xyzz_inf();
-    for (uint32_t j = threadIdx.x; j < per_window; j += RED_THREADS) {
-        G1XYZZ o = load_xyzz(in + (size_t)w * per_window + j);
-        xyzz_add(total, o);
+    const uint32_t set = blockIdx.x;
+    G1XYZZ acc = xyzz_inf();
+    for (int L = (int)lv.nlevels - 1; L >= 0; L--) {
+        G1XYZZ v = xyzz_inf();
+        const G1XYZZ* base = level_partials + lv.offset[L] + (size_t)set * lv.blocks[L];
+        for (uint32_t j = threadIdx.x; j < lv.blocks[L]; j += RED_THREADS) {
+            G1XYZZ o = load_xyzz(base + j);
+            xyzz_add(v, o);
+        }
+        block_tree_sum(v, sh);
+        if (threadIdx.x == 0) {
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) acc = xyzz_dbl(acc);
+            xyzz_add(acc, v);
+        }
     }
-    block_tree_sum(total, sh);
-    if (threadIdx.x == 0) store_xyzz(windows + w, total);
+    if (threadIdx.x == 0) store_xyzz(set_sums + set, acc);
 }
 
-// result = sum_w 2^(c*w) * windows[w]
-__global__ void msm_horner_kernel(const G1XYZZ* __restrict__ windows, MsmGeom g, G1XYZZ* __restrict__ result) {
+// result = sum_w 2^(c*w) * windows[w]   (raw flavour)
+__global__ void msm_horner_kernel(const G1XYZZ* __restrict__ windows, uint32_t nwin, uint32_t c, G1XYZZ* __restrict__ result) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    G1XYZZ acc = load_xyzz(windows + (g.nwin - 1));
-    for (int w = (int)g.nwin - 2; w >= 0; w--) {
-        for (uint32_t k = 0; k < g.c; k++) acc = xyzz_dbl(acc);
+    G1XYZZ acc = load_xyzz(windows + (nwin - 1));
+    for (int w = (int)nwin - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl(acc);
         G1XYZZ o = load_xyzz(windows + w);
         xyzz_add(acc, o);
     }
@@ -390,52 +413,152 @@ __global__ void g1_finish_kernel(const G1XYZZ* __restrict__ parts, uint32_t coun
 }
 
 // ---------------------------------------------------------------------------------------------
+// SRS window table:  T[w][i] = 2^(c w) P_i.   Stage 1 walks the doubling chain of each point in XYZZ and
+// parks every window's value; stage 2 normalises the nwin values of a point with one shared inversion
+// (Montgomery trick over ZZ*ZZZ) and writes the affine table.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) srs_table_chain_kernel(const G1Affine* __restrict__ pts, uint64_t first, uint64_t count,
+                                                              uint32_t c, uint32_t nwin, G1XYZZ* __restrict__ tmp) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    G1Affine p = load_affine(pts + first + t);
+    G1XYZZ acc = xyzz_from_affine(p);
+    for (uint32_t w = 1; w < nwin; w++) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < c; k++) acc = xyzz_dbl(acc);
+        store_xyzz(tmp + (size_t)(w - 1) * count + t, acc);
+    }
+}
+
+__global__ void __launch_bounds__(128) srs_table_normalise_kernel(const G1Affine* __restrict__ pts, uint64_t first,
+                                                                  uint64_t count, uint64_t stride, uint32_t nwin,
+                                                                  const G1XYZZ* __restrict__ tmp, Fq* __restrict__ prefix,
+                                                                  G1Affine* __restrict__ table) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    G1Affine p = load_affine(pts + first + t);
+    fp_store(&table[first + t].x, p.x);
+    fp_store(&table[first + t].y, p.y);
+    if (g1_affine_is_inf(p)) {  // every multiple of the point at infinity is the point at infinity
+        for (uint32_t w = 1; w < nwin; w++) {
+            fp_store(&table[(size_t)w * stride + first + t].x, fp_zero<FqP>());
+            fp_store(&table[(size_t)w * stride + first + t].y, fp_zero<FqP>());
+        }
+        return;
+    }
+    // a point of odd prime order never doubles to infinity: every ZZ*ZZZ below is non-zero
+    Fq run = fp_one<FqP>();
+    for (uint32_t w = 1; w < nwin; w++) {
+        const G1XYZZ* v = tmp + (size_t)(w - 1) * count + t;
+        fp_store(prefix + (size_t)(w - 1) * count + t, run);
+        run = fp_mul(run, fp_mul(fp_load<FqP>(&v->zz), fp_load<FqP>(&v->zzz)));
+    }
+    Fq inv = fp_inv(run);
+    for (uint32_t w = nwin - 1; w >= 1; w--) {
+        const G1XYZZ* v = tmp + (size_t)(w - 1) * count + t;
+        Fq zz = fp_load<FqP>(&v->zz), zzz = fp_load<FqP>(&v->zzz);
+        Fq i_w = fp_mul(inv, fp_load<FqP>(prefix + (size_t)(w - 1) * count + t));  // 1 / (zz zzz)
+        inv = fp_mul(inv, fp_mul(zz, zzz));
+        G1Affine* dst = table + (size_t)w * stride + first + t;
+        fp_store(&dst->x, fp_mul(fp_load<FqP>(&v->x), fp_mul(i_w, zzz)));  // X / ZZ
+        fp_store(&dst->y, fp_mul(fp_load<FqP>(&v->y), fp_mul(i_w, zz)));   // Y / ZZZ
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
-static uint32_t auto_window(uint64_t n) {
+static uint32_t windows_for(uint32_t c, bool montgomery) {
+    // Montgomery sources are reduced (< r < 2^254): ceil(255/c) digits leave the top one carry-free.
+    // Raw standard-form scalars may use all 256 bits: ceil(257/c).
+    const uint32_t bits = montgomery ? 255 : 257;
+    return (bits + c - 1) / c;
+}
+
+// raw flavour: per-window bucket sets, keep the sets small
+static uint32_t auto_window_raw(uint64_t n) {
     uint32_t lg = 0;
     while ((1ull << (lg + 1)) <= n) lg++;
     int c = (int)lg - 4;
     if (c < 4) c = 4;
-    if (c > 16) c = 16;
+    if (c > 17) c = 17;
     return (uint32_t)c;
+}
+
+// table flavour: one bucket set; minimise  n * digits(c) + 3 * 2^(c-1)  (bucket reduction ~ 3 adds per bucket)
+uint32_t msm_table_window(uint64_t n) {
+    uint32_t best = 4;
+    double best_cost = 1e300;
+    for (uint32_t c = 4; c <= 23; c++) {
+        double cost = (double)n * windows_for(c, false) + 3.0 * (double)(1ull << (c - 1));
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static MsmGeom msm_geometry(kzg_ctx* ctx, uint64_t n, bool montgomery) {
+static MsmGeom msm_geometry(kzg_ctx* ctx, const MsmBases& b, uint64_t n, bool montgomery) {
     MsmGeom g;
-    g.c = ctx->msm_window ? ctx->msm_window : auto_window(n);
-    if (g.c < 2) g.c = 2;
-    if (g.c > 22) g.c = 22;
-    // Montgomery sources are reduced (< r < 2^254): ceil(255/c) windows leave the top digit carry-free.
-    // Raw standard-form scalars may use all 256 bits: ceil(257/c).
-    const uint32_t bits = montgomery ? 255 : 257;
-    g.nwin = (bits + g.c - 1) / g.c;
+    if (b.table) {
+        g.c = b.tab_c;
+        g.nwin = windows_for(g.c, montgomery);
+        if (g.nwin > b.tab_nwin) g.nwin = b.tab_nwin;  // (never: the table is built for raw scalars)
+        g.nsets = 1;
+        g.stride = b.stride;
+    } else {
+        g.c = ctx->msm_window ? ctx->msm_window : auto_window_raw(n);
+        if (g.c < 2) g.c = 2;
+        if (g.c > 22) g.c = 22;
+        g.nwin = windows_for(g.c, montgomery);
+        g.nsets = g.nwin;
+        g.stride = 0;
+    }
     g.nbuckets = 1u << (g.c - 1);
     g.seg = 0;
     return g;
 }
 
-int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev) {
+int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev) {
     if (n == 0) {
         KZG_CUDA(ctx, cudaMemsetAsync(result_dev, 0, sizeof(G1XYZZ), ctx->stream));
         return KZG_OK;
     }
     if (n >= (1ull << 27)) return set_err(ctx, KZG_ERR_ARG, "msm: at most 2^27 - 1 points per call");
-    MsmGeom g = msm_geometry(ctx, n, src.montgomery);
-    const uint64_t avg = n / g.nbuckets + 1;
+    MsmGeom g = msm_geometry(ctx, bases, n, src.montgomery);
+    const uint32_t nkeys = g.nsets * g.nbuckets;
+    const uint64_t max_entries = n * g.nwin;
+    if (max_entries >= (1ull << 32)) return set_err(ctx, KZG_ERR_ARG, "msm: n * windows exceeds 2^32 entries");
+    const uint64_t avg = max_entries / nkeys + 1;
     uint64_t seg = 4 * avg;
     if (seg < 256) seg = 256;
     g.seg = (uint32_t)seg;
-    const uint32_t nkeys = g.nwin * g.nbuckets;
-    const uint64_t max_entries = n * g.nwin;
     const uint64_t max_tasks = (uint64_t)nkeys + max_entries / g.seg + 1;
-    if (max_entries >= (1ull << 32)) return set_err(ctx, KZG_ERR_ARG, "msm: n * windows exceeds 2^32 entries");
 
-    const uint32_t red_chunk = g.nbuckets >= 2048 ? 16 : (g.nbuckets >= 128 ? 4 : 1);
-    const uint32_t nch = (g.nbuckets + red_chunk - 1) / red_chunk;
-    const uint32_t red_blocks = (nch + RED_THREADS - 1) / RED_THREADS;
+    // reduction hierarchy
+    RedLevels lv;
+    memset(&lv, 0, sizeof(lv));
+    uint32_t n_in[8], n_out[8];
+    uint32_t part_total = 0;
+    size_t u_total = 0;
+    {
+        uint32_t cur = g.nbuckets;  // weighted elements at this level
+        while (true) {
+            const uint32_t L = lv.nlevels;
+            n_in[L] = cur;
+            n_out[L] = (cur + RED_CHUNK - 1) / RED_CHUNK;
+            lv.blocks[L] = (n_out[L] + RED_THREADS - 1) / RED_THREADS;
+            lv.offset[L] = part_total;
+            part_total += lv.blocks[L] * g.nsets;
+            u_total += (size_t)n_out[L] * g.nsets;
+            lv.nlevels++;
+            if (n_out[L] <= 1 || lv.nlevels == 8) break;
+            cur = n_out[L] - 1;  // element 0 of the next level has weight 0
+        }
+    }
 
     // scratch layout
     size_t off = 0;
@@ -445,8 +568,9 @@ int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G
     const size_t o_segoff = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_sorted = off;   off = align_up(off + sizeof(uint32_t) * max_entries, 256);
     const size_t o_partials = off; off = align_up(off + sizeof(G1XYZZ) * max_tasks, 256);
-    const size_t o_red = off;      off = align_up(off + sizeof(G1XYZZ) * (size_t)g.nwin * red_blocks, 256);
-    const size_t o_windows = off;  off = align_up(off + sizeof(G1XYZZ) * g.nwin, 256);
+    const size_t o_u = off;        off = align_up(off + sizeof(G1XYZZ) * u_total, 256);
+    const size_t o_lp = off;       off = align_up(off + sizeof(G1XYZZ) * part_total, 256);
+    const size_t o_sets = off;     off = align_up(off + sizeof(G1XYZZ) * g.nsets, 256);
     const uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
     const size_t o_tiles = off;    off = align_up(off + sizeof(uint2) * ntiles, 256);
     const size_t o_heavy = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
@@ -459,11 +583,13 @@ int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G
     uint32_t* segoff = (uint32_t*)(sc + o_segoff);
     uint32_t* sorted = (uint32_t*)(sc + o_sorted);
     G1XYZZ* partials = (G1XYZZ*)(sc + o_partials);
-    G1XYZZ* red = (G1XYZZ*)(sc + o_red);
-    G1XYZZ* windows = (G1XYZZ*)(sc + o_windows);
+    G1XYZZ* u_arrays = (G1XYZZ*)(sc + o_u);
+    G1XYZZ* level_partials = (G1XYZZ*)(sc + o_lp);
+    G1XYZZ* set_sums = (G1XYZZ*)(sc + o_sets);
     uint2* tile_sums = (uint2*)(sc + o_tiles);
-    uint32_t* heavy = (uint32_t*)(sc + o_heavy);       // [0] = count, [1..] = keys
+    uint32_t* heavy = (uint32_t*)(sc + o_heavy);  // [0] = count, [1..] = keys
 
+    const G1Affine* pts = bases.table ? bases.table : bases.pts;
     KZG_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nkeys + 1), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), ctx->stream));
     const uint32_t dblocks = (uint32_t)((n + 255) / 256);
@@ -475,12 +601,26 @@ int msm_run(kzg_ctx* ctx, const G1Affine* bases, MsmScalarSrc src, uint64_t n, G
     KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
     const uint32_t ablocks = (uint32_t)((max_tasks + 127) / 128);
     timed_begin(ctx, KZG_TIMED_MSM_ACCUMULATE);
-    KZG_LAUNCH(ctx, msm_accumulate_kernel, ablocks, 128, 0, bases, sorted, offsets, segoff, nkeys, g.seg, partials);
+    KZG_LAUNCH(ctx, msm_accumulate_kernel, ablocks, 128, 0, pts, sorted, offsets, segoff, nkeys, g.seg, partials);
     timed_end(ctx, KZG_TIMED_MSM_ACCUMULATE);
-    KZG_LAUNCH(ctx, msm_collapse_kernel, (uint32_t)ctx->sm_count * 2, COLLAPSE_THREADS, 0, partials, segoff, heavy + 1, heavy);
-    KZG_LAUNCH(ctx, msm_reduce1_kernel, dim3(red_blocks, g.nwin), RED_THREADS, 0, partials, segoff, g, red_chunk, red);
-    KZG_LAUNCH(ctx, msm_reduce2_kernel, g.nwin, RED_THREADS, 0, red, red_blocks, windows);
-    KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, windows, g, result_dev);
+    KZG_LAUNCH(ctx, msm_collapse_kernel, (uint32_t)ctx->sm_count * 2, RED_THREADS, 0, partials, segoff, heavy + 1, heavy);
+    {
+        const G1XYZZ* in = partials;
+        G1XYZZ* u = u_arrays;
+        for (uint32_t L = 0; L < lv.nlevels; L++) {
+            KZG_LAUNCH(ctx, msm_reduce_level_kernel, dim3(lv.blocks[L], g.nsets), RED_THREADS, 0, in,
+                       L == 0 ? segoff : nullptr, n_in[L], L == 0 ? g.nbuckets : n_out[L - 1], L == 0 ? 0u : 1u, u, n_out[L],
+                       level_partials + lv.offset[L]);
+            in = u;
+            u += (size_t)n_out[L] * g.nsets;
+        }
+    }
+    if (g.nsets == 1) {
+        KZG_LAUNCH(ctx, msm_reduce_final_kernel, 1, RED_THREADS, 0, level_partials, lv, result_dev);
+    } else {
+        KZG_LAUNCH(ctx, msm_reduce_final_kernel, g.nsets, RED_THREADS, 0, level_partials, lv, set_sums);
+        KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, result_dev);
+    }
     KZG_CHECK_LAUNCH(ctx);
     return KZG_OK;
 }
@@ -496,6 +636,72 @@ int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t c
     return KZG_OK;
 }
 
+// build (or rebuild) the window table of an SRS; c = 0 picks the window from the SRS size
+int srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t c) {
+    if (srs->table) {
+        KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(srs->table);
+        srs->table = nullptr;
+        srs->tab_c = srs->tab_nwin = 0;
+    }
+    if (srs->n == 0) return KZG_OK;
+    if (c == 0) c = msm_table_window(srs->n);
+    if (c < 2 || c > 23) return set_err(ctx, KZG_ERR_ARG, "srs table window must be in [2, 23]");
+    const uint32_t nwin = windows_for(c, false);
+    if ((uint64_t)nwin * srs->n >= (1ull << 31)) return set_err(ctx, KZG_ERR_ARG, "srs table would exceed 2^31 entries");
+    G1Affine* table = nullptr;
+    cudaError_t e = cudaMalloc((void**)&table, sizeof(G1Affine) * srs->n * nwin);
+    if (e != cudaSuccess)
+        return set_err(ctx, KZG_ERR_NOMEM, std::string("SRS window table allocation failed: ") + cudaGetErrorString(e));
+    const uint64_t chunk = 1ull << 20;  // points per pass (bounds the XYZZ staging buffer)
+    const uint64_t cmax = srs->n < chunk ? srs->n : chunk;
+    G1XYZZ* tmp = nullptr;
+    Fq* prefix = nullptr;
+    if (nwin > 1) {
+        e = cudaMalloc((void**)&tmp, sizeof(G1XYZZ) * cmax * (nwin - 1));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&prefix, sizeof(Fq) * cmax * (nwin - 1));
+        if (e != cudaSuccess) {
+            cudaFree(table);
+            cudaFree(tmp);
+            return set_err(ctx, KZG_ERR_NOMEM, std::string("SRS window table staging allocation failed: ") + cudaGetErrorString(e));
+        }
+    }
+    for (uint64_t first = 0; first < srs->n; first += chunk) {
+        const uint64_t count = srs->n - first < chunk ? srs->n - first : chunk;
+        const uint32_t blocks = (uint32_t)((count + 127) / 128);
+        if (nwin > 1) KZG_LAUNCH(ctx, srs_table_chain_kernel, blocks, 128, 0, srs->d, first, count, c, nwin, tmp);
+        KZG_LAUNCH(ctx, srs_table_normalise_kernel, blocks, 128, 0, srs->d, first, count, srs->n, nwin, tmp, prefix, table);
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    cudaFree(prefix);
+    if (e != cudaSuccess) {
+        cudaFree(table);
+        return set_err(ctx, KZG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    srs->table = table;
+    srs->tab_c = c;
+    srs->tab_nwin = nwin;
+    return KZG_OK;
+}
+
+MsmBases srs_bases(kzg_ctx* ctx, const kzg_srs* srs, uint64_t first) {
+    MsmBases b;
+    b.pts = srs->d + first;
+    b.table = nullptr;
+    b.stride = 0;
+    b.tab_c = b.tab_nwin = 0;
+    // an explicit kzg_msm_set_window() asks for the classic per-window path (tuning / cross-checks)
+    if (srs->table && ctx->msm_window == 0) {
+        b.table = srs->table + first;
+        b.stride = srs->n;
+        b.tab_c = srs->tab_c;
+        b.tab_nwin = srs->tab_nwin;
+    }
+    return b;
+}
+
 }  // namespace kzg
 
 using namespace kzg;
@@ -503,11 +709,21 @@ using namespace kzg;
 // device slot for the XYZZ result of the MSM in flight (inside ctx->dev_small, past the 64-byte affine slot)
 static inline G1XYZZ* result_slot(kzg_ctx* ctx) { return (G1XYZZ*)(ctx->dev_small + 1024); }
 
+static MsmBases raw_bases(const G1Affine* pts) {
+    MsmBases b;
+    b.pts = pts;
+    b.table = nullptr;
+    b.stride = 0;
+    b.tab_c = b.tab_nwin = 0;
+    return b;
+}
+
 extern "C" {
 
-int kzg_msm_geometry(kzg_ctx* ctx, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows) {
+int kzg_msm_geometry(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows) {
     if (!ctx) return KZG_ERR_ARG;
-    MsmGeom g = msm_geometry(ctx, n ? n : 1, montgomery != 0);
+    MsmBases b = srs ? srs_bases(ctx, srs, 0) : raw_bases(nullptr);
+    MsmGeom g = msm_geometry(ctx, b, n ? n : 1, montgomery != 0);
     if (window_bits) *window_bits = g.c;
     if (windows) *windows = g.nwin;
     return KZG_OK;
@@ -518,6 +734,11 @@ int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c) {
     if (c != 0 && (c < 2 || c > 22)) return set_err(ctx, KZG_ERR_ARG, "msm window must be 0 (auto) or in [2, 22]");
     ctx->msm_window = c;
     return KZG_OK;
+}
+
+int kzg_srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t window_bits) {
+    if (!ctx || !srs) return KZG_ERR_ARG;
+    return srs_precompute(ctx, srs, window_bits);
 }
 
 // commit(pol): MSM length = min(len, |SRS|); coefficients beyond the SRS must be zero (the reference
@@ -533,7 +754,7 @@ int kzg_commit(kzg_ctx* ctx, kzg_srs* srs, kzg_buf* coef, uint8_t out_affine[64]
         n = srs->n;
     }
     MsmScalarSrc src{coef->d, true};
-    KZG_TRY(msm_run(ctx, srs->d, src, n, result_slot(ctx)));
+    KZG_TRY(msm_run(ctx, srs_bases(ctx, srs, 0), src, n, result_slot(ctx)));
     return msm_result_to_host_affine(ctx, result_slot(ctx), 1, out_affine);
 }
 
@@ -541,7 +762,7 @@ int kzg_srs_msm(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std
     if (!ctx || !srs || !scalars_std || !out_affine) return KZG_ERR_ARG;
     if (first + n > srs->n || n > scalars_std->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
     MsmScalarSrc src{scalars_std->d, false};
-    KZG_TRY(msm_run(ctx, srs->d + first, src, n, result_slot(ctx)));
+    KZG_TRY(msm_run(ctx, srs_bases(ctx, srs, first), src, n, result_slot(ctx)));
     return msm_result_to_host_affine(ctx, result_slot(ctx), 1, out_affine);
 }
 
@@ -549,12 +770,29 @@ int kzg_srs_msm_partial(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* sca
     if (!ctx || !srs || !scalars_std || !partial_dev) return KZG_ERR_ARG;
     if (first + n > srs->n || n > scalars_std->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
     MsmScalarSrc src{scalars_std->d, false};
-    return msm_run(ctx, srs->d + first, src, n, (G1XYZZ*)partial_dev);
+    return msm_run(ctx, srs_bases(ctx, srs, first), src, n, (G1XYZZ*)partial_dev);
 }
 
 int kzg_g1_partials_combine(kzg_ctx* ctx, const void* partials_dev, uint32_t count, uint8_t out_affine[64]) {
     if (!ctx || !partials_dev || !out_affine || count == 0) return KZG_ERR_ARG;
     return msm_result_to_host_affine(ctx, (const G1XYZZ*)partials_dev, count, out_affine);
+}
+
+// scalars from host memory against a resident SRS (the e2e path of bench.py: H2D of the scalars is inside)
+int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
+                     uint8_t out_affine[64]) {
+    if (!ctx || !srs || (!scalars_std_host && n) || !out_affine) return KZG_ERR_ARG;
+    if (first + n > srs->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
+    Fr* tmp = nullptr;
+    if (n) {
+        KZG_CUDA(ctx, cudaMallocAsync((void**)&tmp, sizeof(Fr) * n, ctx->stream));
+        KZG_CUDA(ctx, cudaMemcpyAsync(tmp, scalars_std_host, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    MsmScalarSrc src{tmp, false};
+    int r = msm_run(ctx, srs_bases(ctx, srs, first), src, n, result_slot(ctx));
+    if (r == KZG_OK) r = msm_result_to_host_affine(ctx, result_slot(ctx), 1, out_affine);
+    if (tmp) cudaFreeAsync(tmp, ctx->stream);
+    return r;
 }
 
 int kzg_g1_msm_affine(kzg_ctx* ctx, const void* bases, const void* scalars_std, uint64_t n, uint32_t flags,
@@ -576,13 +814,13 @@ int kzg_g1_msm_affine(kzg_ctx* ctx, const void* bases, const void* scalars_std, 
         d_scalars = tmp_scalars;
     }
     MsmScalarSrc src{d_scalars, false};
-    r = msm_run(ctx, d_bases, src, n, result_slot(ctx));
+    r = msm_run(ctx, raw_bases(d_bases), src, n, result_slot(ctx));
     if (r == KZG_OK) r = msm_result_to_host_affine(ctx, result_slot(ctx), 1, out_affine);
     if (tmp_bases) cudaFreeAsync(tmp_bases, ctx->stream);
     if (tmp_scalars) cudaFreeAsync(tmp_scalars, ctx->stream);
     if (r == KZG_OK && out_jacobian) {
         // G1.multiExpAffine returns a Jacobian triple (polynomial.js:1112); a triple is not canonical, so the
-        // normalised representative (x, y, 1) -- or (0, 0, 0)... the all-zero triple for infinity -- is returned.
+        // normalised representative (x, y, 1) -- the all-zero triple for infinity -- is returned.
         memcpy(out_jacobian, out_affine, 64);
         bool inf = true;
         for (int i = 0; i < 64; i++) inf &= out_affine[i] == 0;

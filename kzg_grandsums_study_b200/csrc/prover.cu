@@ -135,7 +135,8 @@ using namespace kzg;
 static int dev_alloc(kzg_prover* p, uint64_t count, Fr** out) {
     kzg_ctx* ctx = p->ctx;
     void* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, sizeof(Fr) * (count ? count : 1));
+    // stream-ordered pool allocation: after the first proof the pool serves these without touching the driver
+    cudaError_t e = cudaMallocAsync(&d, sizeof(Fr) * (count ? count : 1), ctx->stream);
     if (e != cudaSuccess) return set_err(ctx, KZG_ERR_NOMEM, std::string("prover allocation failed: ") + cudaGetErrorString(e));
     p->owned.push_back(d);
     *out = (Fr*)d;
@@ -147,7 +148,7 @@ static int commit_dev(kzg_prover* p, const Fr* coef, uint64_t len, uint8_t out[6
     uint64_t npts = len < p->srs->n ? len : p->srs->n;
     G1XYZZ* slot = (G1XYZZ*)(ctx->dev_small + 1024);
     MsmScalarSrc src{coef, true};
-    KZG_TRY(msm_run(ctx, p->srs->d, src, npts, slot));
+    KZG_TRY(msm_run(ctx, srs_bases(ctx, p->srs, 0), src, npts, slot));
     return msm_result_to_host_affine(ctx, slot, 1, out);
 }
 
@@ -167,8 +168,7 @@ uint32_t kzg_prover_n_round1_commitments(kzg_prover* p) { return p ? 2 * p->k + 
 
 int kzg_prover_destroy(kzg_prover* p) {
     if (!p) return KZG_OK;
-    cudaStreamSynchronize(p->ctx->stream);
-    for (void* d : p->owned) cudaFree(d);
+    for (void* d : p->owned) cudaFreeAsync(d, p->ctx->stream);
     delete p;
     return KZG_OK;
 }

@@ -282,6 +282,7 @@ int kzg_srs_free(kzg_ctx* ctx, kzg_srs* srs) {
     if (!srs) return KZG_OK;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     cudaFree(srs->d);
+    cudaFree(srs->table);
     delete srs;
     return KZG_OK;
 }

@@ -331,3 +331,64 @@ def test_commit_large_closed_form(curve, tau, log_n):
         assert bn.g1_add(bn.g1_from_bytes(got), bn.g1_from_bytes(cq)) == bn.g1_from_bytes(cs)
     finally:
         curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+@pytest.mark.parametrize("n,table_c", [(1, 0), (2, 3), (37, 4), (1000, 0), (1000, 9), (5000, 13), (1 << 16, 0), (1 << 16, 17)])
+def test_srs_table_msm(curve, tau, n, table_c):
+    """MSM over a resident SRS with the precomputed window table (single bucket set, radix-16 reduction hierarchy)
+    == the table-less per-window MSM == the closed form; prefixes and offset slices of the SRS included"""
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200._lib import as_ptr
+    srs = C.c_void_p()
+    curve.check(curve.lib.kzg_srs_generate(curve.ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
+    try:
+        scal = synthetic.random_fr_std(900 + n, n)
+        sc = [sum(int(scal[i, j]) << (64 * j) for j in range(4)) for i in range(min(n, 2000))]
+        buf = curve.to_device(scal.tobytes())
+        out_plain, out_tab, out_host = bytearray(64), bytearray(64), bytearray(64)
+        curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out_plain)))
+        curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, table_c))
+        c, w = C.c_uint32(), C.c_uint32()
+        curve.check(curve.lib.kzg_msm_geometry(curve.ctx, srs, n, 0, C.byref(c), C.byref(w)))
+        assert (table_c == 0 or c.value == table_c) and w.value == -(-257 // c.value)
+        curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out_tab)))
+        curve.check(curve.lib.kzg_srs_msm_host(curve.ctx, srs, 0, as_ptr(scal), n, as_ptr(out_host)))
+        assert bytes(out_tab) == bytes(out_plain) == bytes(out_host)
+        if n <= 2000:
+            expect = sum(s * pow(tau, i, R) for i, s in enumerate(sc)) % R
+            assert bytes(out_tab) == bn.g1_to_bytes(bn.g1_mul_gen(expect))
+        if n >= 37:
+            first, m = 5, n - 11          # a slice that starts inside the SRS (the multi-GPU shard shape)
+            a, b = bytearray(64), bytearray(64)
+            curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, first, buf.handle, m, as_ptr(a)))
+            curve.check(curve.lib.kzg_msm_set_window(curve.ctx, 7))       # forces the table-less path
+            curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, first, buf.handle, m, as_ptr(b)))
+            curve.check(curve.lib.kzg_msm_set_window(curve.ctx, 0))
+            assert bytes(a) == bytes(b)
+    finally:
+        curve.check(curve.lib.kzg_msm_set_window(curve.ctx, 0))
+        curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+def test_srs_table_edge_cases(curve):
+    """table over an SRS that contains infinity, repeated and opposite points; skewed scalars (one overfull bucket)"""
+    from kzg_grandsums_study_b200._lib import as_ptr
+    G = bn.g1_to_bytes((1, 2))
+    negG = bn.g1_to_bytes((1, bn.Q - 2))
+    inf = bytes(64)
+    pts = (G + inf + G + negG) * 300
+    n = 1200
+    srs = C.c_void_p()
+    curve.check(curve.lib.kzg_srs_from_host(curve.ctx, as_ptr(pts), n, C.byref(srs)))
+    try:
+        for table_c in (0, 5):
+            curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, table_c))
+            for scalars in ([7] * n, inputs.random_column(3, n), [0] * n, [R - 1] * n, [1 << 253] * n):
+                coeffs = [1, 0, 1, -1] * 300
+                expect = sum(s * c for s, c in zip(scalars, coeffs)) % R
+                buf = curve.to_device(bn.fr_vec_to_std_bytes(scalars))
+                out = bytearray(64)
+                curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out)))
+                assert bytes(out) == bn.g1_to_bytes(bn.g1_mul_gen(expect)), (table_c, scalars[0])
+    finally:
+        curve.lib.kzg_srs_free(curve.ctx, srs)
