@@ -199,10 +199,11 @@ def run_b200(args):
     del scal_all
     scal_dev = curve.alloc(shard)
     curve.check(lib.kzg_buf_upload(ctx, scal_dev.handle, 0, as_ptr(scal_host), shard))
-    partial = torch.zeros(16, dtype=torch.int64, device=dev)        # 128 B XYZZ partial of this rank
-    gathered = torch.zeros(16 * world, dtype=torch.int64, device=dev)
+    from kzg_grandsums_study_b200.sharded_msm import ShardedSrsMsm
+    sharded = ShardedSrsMsm(world, rank, dev, curve=curve, srs=srs)
     out_affine = bytearray(64)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    scal_stage = curve.alloc(shard)
 
     def barrier():
         if world > 1:
@@ -213,11 +214,7 @@ def run_b200(args):
         if world == 1:
             curve.check(lib.kzg_srs_msm(ctx, srs, 0, scal_dev.handle, shard, as_ptr(out_affine)))
         else:
-            curve.check(lib.kzg_srs_msm_partial(ctx, srs, 0, scal_dev.handle, shard, as_ptr(partial)))
-            dist.all_gather_into_tensor(gathered, partial)
-            curve.check(lib.kzg_g1_partials_combine(ctx, as_ptr(gathered), world, as_ptr(out_affine)))
-
-    scal_stage = curve.alloc(shard)
+            out_affine[:] = sharded.msm(scal_dev.handle, shard)
 
     def step_e2e():
         # the call a host binding makes: scalars in (pinned) host memory, bases = the resident SRS shard
@@ -225,9 +222,7 @@ def run_b200(args):
             curve.check(lib.kzg_srs_msm_host(ctx, srs, 0, as_ptr(scal_host), shard, as_ptr(out_affine)))
         else:
             curve.check(lib.kzg_buf_upload(ctx, scal_stage.handle, 0, as_ptr(scal_host), shard))
-            curve.check(lib.kzg_srs_msm_partial(ctx, srs, 0, scal_stage.handle, shard, as_ptr(partial)))
-            dist.all_gather_into_tensor(gathered, partial)
-            curve.check(lib.kzg_g1_partials_combine(ctx, as_ptr(gathered), world, as_ptr(out_affine)))
+            out_affine[:] = sharded.msm(scal_stage.handle, shard)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -274,12 +269,19 @@ def run_b200(args):
     if bytes(out_affine) != result_resident:
         raise SystemExit("bench.py: e2e result differs from the resident-input result")
 
-    # ---- known answer: sum s_i tau^i * G1, checked with the library's own evaluate + one fixed-base product ----
-    check = None
-    if rank == 0 and world == 1:
-        check = verify_known_answer(curve, scal_dev, tau, result_resident)
-        if not check:
-            raise SystemExit("bench.py: MSM result does not match the closed form (sum s_i tau^i) G1")
+    # ---- known answer: (sum s_i tau^i) G1 -- per-shard sums by the library's own Horner kernel, added on the host ----
+    k_shard = shard_known_scalar(curve, scal_dev, tau, first)
+    if world > 1:
+        ks = torch.tensor([(k_shard >> (62 * j)) & ((1 << 62) - 1) for j in range(5)], dtype=torch.int64, device=dev)
+        allk = torch.zeros(5 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allk, ks)
+        allk = allk.cpu().tolist()
+        k_total = sum(sum(allk[5 * g + j] << (62 * j) for j in range(5)) for g in range(world)) % curve.r
+    else:
+        k_total = k_shard
+    check = known_answer_matches(curve, k_total, result_resident)
+    if not check:
+        raise SystemExit("bench.py: MSM result does not match the closed form (sum s_i tau^i) G1")
 
     # ---- roofline of the dominant kernel (bucket accumulation), measured live ----
     imad = C.c_double()
@@ -365,17 +367,21 @@ def msm_geometry(lib, ctx, srs, n):
     return {"c": c.value, "windows": w.value}
 
 
-def verify_known_answer(curve, scal_dev, tau, got_affine):
-    """sum_i s_i tau^i by the device Horner evaluation (scalars re-read as Montgomery residues s_i/R), then
-    (R * that) * G1 by a 1-point MSM on the generator"""
+def shard_known_scalar(curve, scal_dev, tau, first):
+    """sum_i s_i tau^(first + i) mod r for this rank's shard, by the device Horner evaluation.  The standard-form
+    scalars are re-read as Montgomery residues (value s_i / 2^256) and the result comes back as Montgomery bytes,
+    i.e. the raw little-endian integer is exactly sum s_i tau^i."""
     from kzg_grandsums_study_b200._lib import as_ptr
     R = curve.r
     out = bytearray(32)
     tau_m = (tau << 256) % R
     curve.check(curve.lib.kzg_poly_evaluate(curve.ctx, scal_dev.handle, as_ptr(tau_m.to_bytes(32, "little")), as_ptr(out)))
-    # evaluate() treats s_i as Montgomery (value s_i / 2^256) and returns Montgomery bytes of sum (s_i/2^256) tau^i,
-    # i.e. the raw little-endian integer is exactly sum s_i tau^i mod r
-    k = int.from_bytes(out, "little") % R
+    return int.from_bytes(out, "little") % R * pow(tau, first, R) % R
+
+
+def known_answer_matches(curve, k, got_affine):
+    """k * G1 by a 1-point MSM on the generator == got_affine"""
+    from kzg_grandsums_study_b200._lib import as_ptr
     gen = ((1 << 256) % curve.q).to_bytes(32, "little") + ((2 << 256) % curve.q).to_bytes(32, "little")
     aff = bytearray(64)
     curve.check(curve.lib.kzg_g1_msm_affine(curve.ctx, as_ptr(gen), as_ptr(k.to_bytes(32, "little")), 1, 0, as_ptr(aff), None))

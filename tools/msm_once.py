@@ -21,8 +21,10 @@ tau = synthetic.tau_from_seed(1001)
 srs = C.c_void_p()
 curve.check(lib.kzg_srs_generate(ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
 scal = curve.to_device(synthetic.random_fr_std(6, n).tobytes())
-if window:
-    curve.check(lib.kzg_msm_set_window(ctx, window))
+if window > 0:
+    curve.check(lib.kzg_msm_set_window(ctx, window))       # per-window (table-less) path
+else:
+    curve.check(lib.kzg_srs_precompute(ctx, srs, -window))  # window table; 0 = auto, -c = table with c bits
 out = bytearray(64)
 for i in range(reps):
     torch.cuda.synchronize()
