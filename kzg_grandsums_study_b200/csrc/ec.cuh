@@ -148,7 +148,9 @@ KZG_HD void xyzz_add(G1XYZZ& acc, const G1XYZZ& b) {
 // k * p for a small non-negative integer k (double-and-add, MSB first)
 KZG_HD G1XYZZ xyzz_mul_small(const G1XYZZ& p, uint32_t k) {
     G1XYZZ r = xyzz_inf();
-    for (int bit = 31; bit >= 0; bit--) {
+    int top = 31;
+    while (top >= 0 && !((k >> top) & 1)) top--;  // skip the leading zeros: no work on the point at infinity
+    for (int bit = top; bit >= 0; bit--) {
         r = xyzz_dbl(r);
         if ((k >> bit) & 1) xyzz_add(r, p);
     }

@@ -13,12 +13,13 @@
 // Pipeline (one stream, no host round trip until the 64-byte result is read):
 //   1. msm_digits<count>  scalars -> signed c-bit digits (leaving Montgomery form first when the source is a
 //                         polynomial: Fr.batchFromMontgomery fused), histogram of bucket keys (L2 atomics)
-//   2. msm_scan_*         exclusive prefix sums of bucket sizes and of per-bucket task counts (3 small launches)
+//   2. msm_scan_*         exclusive prefix sums of bucket sizes, then of partial-sum slots per bucket (2 x 3 launches)
 //   3. msm_digits<scatter> counting-sort scatter of (point index | sign) into bucket order
-//   4. msm_accumulate     one thread per task (a bucket, or a slice of an overfull one): XYZZ += affine over its
-//                         slice of the sorted list; random 64 B gathers, next point prefetched during the add.
+//   4. msm_accumulate     one thread per fixed-length SLICE of the sorted list (equal work per lane whatever the
+//                         bucket sizes): XYZZ += affine, parking a partial sum at every bucket boundary; random 64 B
+//                         gathers, next point prefetched during the add.
 //                         THE IMAD-bound kernel: 10 modmul (1360 limb MACs) per entry.
-//   5. msm_collapse       buckets that were split over several tasks: block-parallel sum of their partials
+//   5. msm_collapse       buckets spread over many slices: block-parallel sum of their partials
 //   6. msm_reduce_level   sum_b (b+1) S_b by a radix-16 hierarchy: each level folds 16 consecutive buckets into a
 //                         weighted partial (running-sum trick) and a plain sum that feeds the next level
 //   7. msm_reduce_final   Horner over the levels (4 doublings each) -> one XYZZ per bucket set
@@ -40,7 +41,7 @@ struct MsmGeom {
     uint32_t nwin;      // digits per scalar
     uint32_t nbuckets;  // buckets per set = 2^(c-1)
     uint32_t nsets;     // bucket sets: 1 with a precomputed table, nwin without
-    uint32_t seg;       // max entries per accumulate task
+    uint32_t seg;       // slice length: entries per accumulate thread
     uint64_t stride;    // table flavour: entry = w * stride + i
 };
 
@@ -53,14 +54,20 @@ __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, uint32_t pos,
     return (uint32_t)(v >> off) & ((1u << c) - 1u);
 }
 
+// Warp-aggregated bucket atomics: lanes of a warp that hit the same key in the same window issue ONE atomic
+// (uniform scalars never collide, but skewed inputs -- equal scalars, a short top window -- would otherwise
+// serialise millions of atomics on a handful of L2 addresses).
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ scalars, uint64_t n, bool montgomery,
                                                          MsmGeom g, uint32_t* __restrict__ counts_or_cursor,
                                                          uint32_t* __restrict__ sorted) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr s = fp_load<FrP>(scalars + i);
-    if (montgomery) s = fp_from_mont(s);
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    Fr s = fp_zero<FrP>();  // lanes past the end run the loop with a zero scalar: the warp stays converged
+    if (i < n) {
+        s = fp_load<FrP>(scalars + i);
+        if (montgomery) s = fp_from_mont(s);
+    }
     uint32_t carry = 0;
     const uint32_t half = g.nbuckets;  // 2^(c-1)
     const bool table = g.nsets == 1;
@@ -76,135 +83,133 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
             neg = 0;
             carry = 0;
         }
-        if (mag != 0) {
-            uint32_t key = (table ? 0u : w * g.nbuckets) + (mag - 1);
-            if (SCATTER) {
-                uint32_t pos = atomicAdd(&counts_or_cursor[key], 1u);
+        const bool valid = mag != 0;
+        const uint32_t key = valid ? (table ? 0u : w * g.nbuckets) + (mag - 1) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t leader = __ffs(peers) - 1;
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (valid && lane == leader) base = atomicAdd(&counts_or_cursor[key], (uint32_t)__popc(peers));
+        if (SCATTER) {
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid) {
                 uint32_t entry = table ? (uint32_t)(w * g.stride + i) : (uint32_t)i;
-                sorted[pos] = entry | (neg << 31);
-            } else {
-                atomicAdd(&counts_or_cursor[key], 1u);
+                sorted[base + rank] = entry | (neg << 31);
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// scan of bucket sizes: offsets[k] = sum_{j<k} counts[j], segoff[k] = sum_{j<k} ceil(counts[j]/seg)
-// Three phases over tiles of SCAN_TILE keys: tile sums, one-block scan of the tile sums, apply.
-// Buckets that need more than one accumulate task are appended to `heavy` (collapsed after accumulation).
+// Exclusive scans over the bucket keys, three phases over tiles of SCAN_TILE keys (tile sums, one-block scan
+// of the tile sums, apply).  Run twice:
+//   mode 0  f(k) = counts[k]                      -> offsets[] (and the scatter cursors)
+//   mode 1  f(k) = slices touched by bucket k     -> pbase[]   (first partial-sum slot of the bucket)
+// The sorted entry list is cut into slices of `slice` entries, one accumulate thread each, so a bucket that
+// spans slice boundaries produces one partial sum per slice it touches.  Buckets with more than
+// HEAVY_PARTS partials are appended to `heavy` and summed by a whole block after the accumulation.
 // ---------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_PER_THREAD = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+constexpr uint32_t HEAVY_PARTS = 8;
 
-__device__ __forceinline__ uint2 block_scan_pair(uint2 v, uint2* sh, uint2& total) {
-    // inclusive scan of (a, b) pairs across the block
+__device__ __forceinline__ uint32_t parts_of(uint32_t off, uint32_t cnt, uint32_t slice) {
+    return cnt == 0 ? 0u : (off + cnt - 1) / slice - off / slice + 1;
+}
+__device__ __forceinline__ uint32_t scan_input(int mode, const uint32_t* __restrict__ counts,
+                                               const uint32_t* __restrict__ offsets, uint32_t k, uint32_t slice) {
+    uint32_t cnt = counts[k];
+    return mode == 0 ? cnt : parts_of(offsets[k], cnt, slice);
+}
+
+__device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t* sh, uint32_t& total) {
+    // inclusive scan across the block
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1) {
-        uint32_t oa = __shfl_up_sync(0xffffffffu, v.x, d), ob = __shfl_up_sync(0xffffffffu, v.y, d);
-        if (lane >= d) {
-            v.x += oa;
-            v.y += ob;
-        }
+        uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
     }
     if (lane == 31) sh[wid] = v;
     __syncthreads();
-    uint2 carry = make_uint2(0, 0), tot = make_uint2(0, 0);
+    uint32_t carry = 0, tot = 0;
 #pragma unroll
     for (int w = 0; w < SCAN_THREADS / 32; w++) {
-        uint2 x = sh[w];
-        if (w < (int)wid) {
-            carry.x += x.x;
-            carry.y += x.y;
-        }
-        tot.x += x.x;
-        tot.y += x.y;
+        uint32_t x = sh[w];
+        if (w < (int)wid) carry += x;
+        tot += x;
     }
     __syncthreads();
     total = tot;
-    return make_uint2(v.x + carry.x, v.y + carry.y);
+    return v + carry;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t nkeys,
-                                                                      uint32_t seg, uint2* __restrict__ tile_sums) {
-    __shared__ uint2 sh[SCAN_THREADS / 32];
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_tiles_kernel(int mode, const uint32_t* __restrict__ counts,
+                                                                      const uint32_t* __restrict__ offsets, uint32_t nkeys,
+                                                                      uint32_t slice, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x;
-    uint2 acc = make_uint2(0, 0);
+    uint32_t acc = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         uint32_t i = base + k * SCAN_THREADS;
-        if (i < nkeys) {
-            uint32_t cnt = counts[i];
-            acc.x += cnt;
-            acc.y += (cnt + seg - 1) / seg;
-        }
+        if (i < nkeys) acc += scan_input(mode, counts, offsets, i, slice);
     }
-    uint2 tot;
-    block_scan_pair(acc, sh, tot);
+    uint32_t tot;
+    block_scan_u32(acc, sh, tot);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 
-// single block: exclusive scan of the tile sums in place; totals -> offsets[nkeys], segoff[nkeys]
-__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_sums_kernel(uint2* __restrict__ tile_sums, uint32_t ntiles,
-                                                                     uint32_t nkeys, uint32_t* __restrict__ offsets,
-                                                                     uint32_t* __restrict__ segoff) {
-    __shared__ uint2 sh[SCAN_THREADS / 32];
-    __shared__ uint2 carry_sh;
-    if (threadIdx.x == 0) carry_sh = make_uint2(0, 0);
+// single block: exclusive scan of the tile sums in place; grand total -> out[nkeys]
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_sums_kernel(uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+                                                                     uint32_t nkeys, uint32_t* __restrict__ out) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32];
+    __shared__ uint32_t carry_sh;
+    if (threadIdx.x == 0) carry_sh = 0;
     __syncthreads();
     for (uint32_t start = 0; start < ntiles; start += SCAN_THREADS) {
         uint32_t i = start + threadIdx.x;
-        uint2 v = i < ntiles ? tile_sums[i] : make_uint2(0, 0);
-        uint2 tot;
-        uint2 inc = block_scan_pair(v, sh, tot);
-        uint2 c = carry_sh;
-        if (i < ntiles) tile_sums[i] = make_uint2(c.x + inc.x - v.x, c.y + inc.y - v.y);
+        uint32_t v = i < ntiles ? tile_sums[i] : 0;
+        uint32_t tot;
+        uint32_t inc = block_scan_u32(v, sh, tot);
+        uint32_t c = carry_sh;
+        if (i < ntiles) tile_sums[i] = c + inc - v;
         __syncthreads();
-        if (threadIdx.x == 0) carry_sh = make_uint2(c.x + tot.x, c.y + tot.y);
+        if (threadIdx.x == 0) carry_sh = c + tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        offsets[nkeys] = carry_sh.x;
-        segoff[nkeys] = carry_sh.y;
-    }
+    if (threadIdx.x == 0) out[nkeys] = carry_sh;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(const uint32_t* __restrict__ counts, uint32_t nkeys,
-                                                                      uint32_t seg, const uint2* __restrict__ tile_sums,
-                                                                      uint32_t* __restrict__ offsets,
-                                                                      uint32_t* __restrict__ cursor,
-                                                                      uint32_t* __restrict__ segoff,
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, const uint32_t* __restrict__ counts,
+                                                                      const uint32_t* __restrict__ offsets, uint32_t nkeys,
+                                                                      uint32_t slice, const uint32_t* __restrict__ tile_sums,
+                                                                      uint32_t* __restrict__ out, uint32_t* __restrict__ cursor,
                                                                       uint32_t* __restrict__ heavy,
                                                                       uint32_t* __restrict__ heavy_count) {
-    __shared__ uint2 sh[SCAN_THREADS / 32];
+    __shared__ uint32_t sh[SCAN_THREADS / 32];
     // thread owns SCAN_PER_THREAD consecutive keys so that its partial results are a running sum
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
-    uint32_t cnt[SCAN_PER_THREAD];
-    uint2 acc = make_uint2(0, 0);
+    uint32_t val[SCAN_PER_THREAD];
+    uint32_t acc = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         uint32_t i = base + k;
-        cnt[k] = i < nkeys ? counts[i] : 0;
-        acc.x += cnt[k];
-        acc.y += (cnt[k] + seg - 1) / seg;
+        val[k] = i < nkeys ? scan_input(mode, counts, offsets, i, slice) : 0;
+        acc += val[k];
     }
-    uint2 tot;
-    uint2 inc = block_scan_pair(acc, sh, tot);
-    uint2 t0 = tile_sums[blockIdx.x];
-    uint32_t ra = t0.x + inc.x - acc.x, rb = t0.y + inc.y - acc.y;
+    uint32_t tot;
+    uint32_t inc = block_scan_u32(acc, sh, tot);
+    uint32_t run = tile_sums[blockIdx.x] + inc - acc;
 #pragma unroll
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         uint32_t i = base + k;
         if (i < nkeys) {
-            offsets[i] = ra;
-            cursor[i] = ra;
-            segoff[i] = rb;
-            uint32_t nseg = (cnt[k] + seg - 1) / seg;
-            if (nseg > 1) heavy[atomicAdd(heavy_count, 1u)] = i;
-            ra += cnt[k];
-            rb += nseg;
+            out[i] = run;
+            if (mode == 0) cursor[i] = run;
+            if (mode == 1 && val[k] > HEAVY_PARTS) heavy[atomicAdd(heavy_count, 1u)] = i;
+            run += val[k];
         }
     }
 }
@@ -237,29 +242,42 @@ __device__ __forceinline__ G1XYZZ load_xyzz(const G1XYZZ* p) {
     return v;
 }
 
+// One thread per slice of `slice` consecutive entries of the sorted list: equal work per lane no matter how
+// the bucket sizes fluctuate.  Whenever the walk crosses a bucket boundary the running sum is parked in the
+// partial-sum slot of (bucket, slice):  pbase[key] + (slice index - first slice of the bucket).
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __restrict__ bases,
                                                              const uint32_t* __restrict__ sorted,
                                                              const uint32_t* __restrict__ offsets,
-                                                             const uint32_t* __restrict__ segoff, uint32_t nkeys,
-                                                             uint32_t seg, G1XYZZ* __restrict__ partials) {
+                                                             const uint32_t* __restrict__ pbase, uint32_t nkeys,
+                                                             uint32_t slice, G1XYZZ* __restrict__ partials) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t ntasks = segoff[nkeys];
-    if (t >= ntasks) return;
-    // largest key with segoff[key] <= t  (segoff is non-decreasing; empty buckets repeat a value)
-    uint32_t lo = 0, hi = nkeys;  // invariant: segoff[lo] <= t < segoff[hi]
+    const uint32_t total = offsets[nkeys];
+    const uint64_t begin64 = (uint64_t)t * slice;
+    if (begin64 >= total) return;
+    const uint32_t begin = (uint32_t)begin64;
+    const uint32_t end = (uint32_t)min((uint64_t)total, begin64 + slice);
+    // bucket of the first entry: largest key with offsets[key] <= begin (empty buckets repeat an offset: the
+    // largest such key is the non-empty one)
+    uint32_t lo = 0, hi = nkeys;  // invariant: offsets[lo] <= begin < offsets[hi]
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (segoff[mid] <= t) lo = mid; else hi = mid;
+        if (offsets[mid] <= begin) lo = mid; else hi = mid;
     }
-    const uint32_t key = lo;
-    const uint32_t s = t - segoff[key];
-    uint32_t begin = offsets[key] + s * seg;
-    uint32_t end = min(begin + seg, offsets[key + 1]);
+    uint32_t key = lo;
+    uint32_t key_end = offsets[key + 1];
 
     G1XYZZ acc = xyzz_inf();
     uint32_t e = sorted[begin];
     G1Affine p = load_affine(bases + (e & 0x7fffffffu));
     for (uint32_t j = begin; j < end; j++) {
+        if (j == key_end) {  // bucket boundary inside the slice
+            store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
+            acc = xyzz_inf();
+            do {
+                key++;
+                key_end = offsets[key + 1];
+            } while (key_end <= j);
+        }
         // prefetch the next entry while this one is being added
         uint32_t e_next = e;
         G1Affine p_next = p;
@@ -272,11 +290,12 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
         e = e_next;
         p = p_next;
     }
-    store_xyzz(partials + t, acc);
+    store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
 }
 
-// After accumulation a bucket that was split over several tasks holds several partial sums: one block per
-// such bucket tree-sums them in shared memory and leaves the total in the bucket's first slot.
+// A bucket that spans many slices holds many partial sums: one block per such bucket tree-sums them in shared
+// memory and leaves the total in the bucket's first slot.  (Buckets with <= HEAVY_PARTS partials are summed by
+// the reader, load_bucket.)
 constexpr int RED_THREADS = 128;
 
 __device__ __forceinline__ void block_tree_sum(G1XYZZ& v, G1XYZZ* sh) {
@@ -297,14 +316,14 @@ __device__ __forceinline__ void block_tree_sum(G1XYZZ& v, G1XYZZ* sh) {
 }
 
 __global__ void __launch_bounds__(RED_THREADS) msm_collapse_kernel(G1XYZZ* __restrict__ partials,
-                                                                   const uint32_t* __restrict__ segoff,
+                                                                   const uint32_t* __restrict__ pbase,
                                                                    const uint32_t* __restrict__ heavy,
                                                                    const uint32_t* __restrict__ heavy_count) {
     __shared__ G1XYZZ sh[RED_THREADS];
     const uint32_t nheavy = *heavy_count;
     for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
         const uint32_t key = heavy[h];
-        const uint32_t a = segoff[key], b = segoff[key + 1];
+        const uint32_t a = pbase[key], b = pbase[key + 1];
         G1XYZZ v = xyzz_inf();
         for (uint32_t j = a + threadIdx.x; j < b; j += RED_THREADS) {
             G1XYZZ o = load_xyzz(partials + j);
@@ -343,8 +362,14 @@ __global__ void __launch_bounds__(RED_THREADS) msm_reduce_level_kernel(const G1X
             G1XYZZ s;
             if (segoff) {
                 const uint32_t key = set * in_stride + b;
-                const uint32_t a = segoff[key];
-                s = a == segoff[key + 1] ? xyzz_inf() : load_xyzz(in + a);
+                const uint32_t a = segoff[key], nparts = segoff[key + 1] - a;
+                s = nparts == 0 ? xyzz_inf() : load_xyzz(in + a);
+                if (nparts > 1 && nparts <= HEAVY_PARTS) {
+                    for (uint32_t j = 1; j < nparts; j++) {
+                        G1XYZZ o = load_xyzz(in + a + j);
+                        xyzz_add(s, o);
+                    }
+                }
             } else {
                 s = load_xyzz(in + (size_t)set * in_stride + b + shift);
             }
@@ -357,10 +382,25 @@ __global__ void __launch_bounds__(RED_THREADS) msm_reduce_level_kernel(const G1X
     if (threadIdx.x == 0) store_xyzz(level_partials + (size_t)set * gridDim.x + blockIdx.x, tot);
 }
 
+// Tail of the hierarchy: once few elements are left, every thread scales its element by its weight q
+// (double-and-add, <= 15 bits) and the block tree-sums them -- log depth instead of more serial levels.
+constexpr uint32_t RED_DIRECT_MAX = 32768;
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_direct_kernel(const G1XYZZ* __restrict__ in, uint32_t n_in,
+                                                                        G1XYZZ* __restrict__ direct_partials) {
+    __shared__ G1XYZZ sh[RED_THREADS];
+    const uint32_t set = blockIdx.y;
+    const uint32_t q = blockIdx.x * RED_THREADS + threadIdx.x;
+    G1XYZZ v = xyzz_inf();
+    if (q >= 1 && q < n_in) v = xyzz_mul_small(load_xyzz(in + (size_t)set * n_in + q), q);
+    block_tree_sum(v, sh);
+    if (threadIdx.x == 0) store_xyzz(direct_partials + (size_t)set * gridDim.x + blockIdx.x, v);
+}
+
 struct RedLevels {
     uint32_t nlevels;
     uint32_t blocks[8];   // block partials per set at each level
     uint32_t offset[8];   // start of the level inside level_partials (in units of G1XYZZ, per-set blocks contiguous)
+    uint32_t direct_blocks, direct_offset;  // partials of the direct tail (0 blocks: none)
 };
 
 // grid = nsets: Horner over the levels, 4 doublings (x16) per level
@@ -369,6 +409,16 @@ __global__ void __launch_bounds__(RED_THREADS) msm_reduce_final_kernel(const G1X
     __shared__ G1XYZZ sh[RED_THREADS];
     const uint32_t set = blockIdx.x;
     G1XYZZ acc = xyzz_inf();
+    if (lv.direct_blocks) {
+        G1XYZZ v = xyzz_inf();
+        const G1XYZZ* base = level_partials + lv.direct_offset + (size_t)set * lv.direct_blocks;
+        for (uint32_t j = threadIdx.x; j < lv.direct_blocks; j += RED_THREADS) {
+            G1XYZZ o = load_xyzz(base + j);
+            xyzz_add(v, o);
+        }
+        block_tree_sum(v, sh);
+        if (threadIdx.x == 0) acc = v;
+    }
     for (int L = (int)lv.nlevels - 1; L >= 0; L--) {
         G1XYZZ v = xyzz_inf();
         const G1XYZZ* base = level_partials + lv.offset[L] + (size_t)set * lv.blocks[L];
@@ -532,11 +582,13 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const uint32_t nkeys = g.nsets * g.nbuckets;
     const uint64_t max_entries = n * g.nwin;
     if (max_entries >= (1ull << 32)) return set_err(ctx, KZG_ERR_ARG, "msm: n * windows exceeds 2^32 entries");
-    const uint64_t avg = max_entries / nkeys + 1;
-    uint64_t seg = 4 * avg;
-    if (seg < 256) seg = 256;
-    g.seg = (uint32_t)seg;
-    const uint64_t max_tasks = (uint64_t)nkeys + max_entries / g.seg + 1;
+    // slice length: about one average bucket, clamped to [16, 128] entries per accumulate thread
+    uint64_t slice = max_entries / nkeys + 1;
+    if (slice < 16) slice = 16;
+    if (slice > 128) slice = 128;
+    g.seg = (uint32_t)slice;
+    const uint64_t max_tasks = (max_entries + slice - 1) / slice;
+    const uint64_t max_parts = max_tasks + nkeys + 1;
 
     // reduction hierarchy
     RedLevels lv;
@@ -544,6 +596,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     uint32_t n_in[8], n_out[8];
     uint32_t part_total = 0;
     size_t u_total = 0;
+    uint32_t direct_n = 0;  // elements handed to the direct tail (index = weight)
     {
         uint32_t cur = g.nbuckets;  // weighted elements at this level
         while (true) {
@@ -555,7 +608,14 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
             part_total += lv.blocks[L] * g.nsets;
             u_total += (size_t)n_out[L] * g.nsets;
             lv.nlevels++;
-            if (n_out[L] <= 1 || lv.nlevels == 8) break;
+            if (n_out[L] <= 1) break;
+            if (n_out[L] <= RED_DIRECT_MAX || lv.nlevels == 8) {
+                direct_n = n_out[L];
+                lv.direct_blocks = (direct_n + RED_THREADS - 1) / RED_THREADS;
+                lv.direct_offset = part_total;
+                part_total += lv.direct_blocks * g.nsets;
+                break;
+            }
             cur = n_out[L] - 1;  // element 0 of the next level has weight 0
         }
     }
@@ -567,12 +627,12 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const size_t o_cursor = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_segoff = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_sorted = off;   off = align_up(off + sizeof(uint32_t) * max_entries, 256);
-    const size_t o_partials = off; off = align_up(off + sizeof(G1XYZZ) * max_tasks, 256);
+    const size_t o_partials = off; off = align_up(off + sizeof(G1XYZZ) * max_parts, 256);
     const size_t o_u = off;        off = align_up(off + sizeof(G1XYZZ) * u_total, 256);
     const size_t o_lp = off;       off = align_up(off + sizeof(G1XYZZ) * part_total, 256);
     const size_t o_sets = off;     off = align_up(off + sizeof(G1XYZZ) * g.nsets, 256);
     const uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
-    const size_t o_tiles = off;    off = align_up(off + sizeof(uint2) * ntiles, 256);
+    const size_t o_tiles = off;    off = align_up(off + sizeof(uint32_t) * ntiles, 256);
     const size_t o_heavy = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     void* base = nullptr;
     KZG_TRY(ctx_scratch(ctx, off, &base));
@@ -586,7 +646,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     G1XYZZ* u_arrays = (G1XYZZ*)(sc + o_u);
     G1XYZZ* level_partials = (G1XYZZ*)(sc + o_lp);
     G1XYZZ* set_sums = (G1XYZZ*)(sc + o_sets);
-    uint2* tile_sums = (uint2*)(sc + o_tiles);
+    uint32_t* tile_sums = (uint32_t*)(sc + o_tiles);
     uint32_t* heavy = (uint32_t*)(sc + o_heavy);  // [0] = count, [1..] = keys
 
     const G1Affine* pts = bases.table ? bases.table : bases.pts;
@@ -594,9 +654,13 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), ctx->stream));
     const uint32_t dblocks = (uint32_t)((n + 255) / 256);
     KZG_LAUNCH(ctx, msm_digits_kernel<false>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, counts, nullptr);
-    KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, nkeys, g.seg, tile_sums);
-    KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, offsets, segoff);
-    KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, counts, nkeys, g.seg, tile_sums, offsets, cursor, segoff,
+    KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums);
+    KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, offsets);
+    KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums,
+               offsets, cursor, heavy + 1, heavy);
+    KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums);
+    KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, segoff);
+    KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums, segoff, cursor,
                heavy + 1, heavy);
     KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
     const uint32_t ablocks = (uint32_t)((max_tasks + 127) / 128);
@@ -614,6 +678,9 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
             in = u;
             u += (size_t)n_out[L] * g.nsets;
         }
+        if (lv.direct_blocks)
+            KZG_LAUNCH(ctx, msm_reduce_direct_kernel, dim3(lv.direct_blocks, g.nsets), RED_THREADS, 0, in, direct_n,
+                       level_partials + lv.direct_offset);
     }
     if (g.nsets == 1) {
         KZG_LAUNCH(ctx, msm_reduce_final_kernel, 1, RED_THREADS, 0, level_partials, lv, result_dev);
