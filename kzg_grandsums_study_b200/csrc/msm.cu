@@ -20,9 +20,11 @@
 //                         gathers, next point prefetched during the add.
 //                         THE IMAD-bound kernel: 10 modmul (1360 limb MACs) per entry.
 //   5. msm_collapse       buckets spread over many slices: block-parallel sum of their partials
-//   6. msm_reduce_level   sum_b (b+1) S_b by a radix-16 hierarchy: each level folds 16 consecutive buckets into a
-//                         weighted partial (running-sum trick) and a plain sum that feeds the next level
-//   7. msm_reduce_final   Horner over the levels (4 doublings each) -> one XYZZ per bucket set
+//   6. msm_reduce_level   sum_b (b+1) S_b by a radix-4..16 hierarchy: each level folds r consecutive buckets into a
+//                         weighted partial (running-sum trick) and a plain sum that feeds the next level;
+//      msm_reduce_direct  the last <= 4096 elements: weight applied by double-and-add
+//   7. msm_reduce_gather  all the partials of all levels summed under a per-thread Horner recurrence over the
+//      msm_reduce_final   levels (log2 r doublings each) -> one XYZZ per bucket set
 //   8. msm_horner         raw flavour only: combine the windows (c doublings each)
 //   9. g1_finish          sum `count` partial points (count > 1 only for the multi-GPU gather), canonical affine
 // The result is a canonical group element, so it is byte-identical to the reference's regardless of window
@@ -335,104 +337,111 @@ __global__ void __launch_bounds__(RED_THREADS) msm_collapse_kernel(G1XYZZ* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// bucket reduction: per set  sum_{b < B} (b+1) S_b , radix-16 hierarchy.
-// With b = 16 q + r:  (b+1) S_b = (r+1) S_b + 16 q S_b, so one level computes, per chunk q of 16 buckets,
-//   t_q = sum_r (r+1) S_{16q+r}   (running-sum trick; block-summed into `level_partials`)
-//   U_q = sum_r S_{16q+r}         (written out: the next level reduces sum_q q U_q = sum_{b'} (b'+1) U_{b'+1})
-// and  total = T_0 + 16 (T_1 + 16 (T_2 + ...)),  T_L = sum_q t_q at level L.
+// bucket reduction: per set  sum_{b < B} (b+1) S_b  as a hierarchy of radix-2^k levels.
+// With b = r q + j (r = 2^k):  (b+1) S_b = (j+1) S_b + r q S_b, so one level computes, per chunk q of r buckets,
+//   t_q = sum_j (j+1) S_{rq+j}   (running-sum trick; block-summed into `level_partials`)
+//   U_q = sum_j S_{rq+j}         (written out: the next level reduces sum_q q U_q = sum_{b'} (b'+1) U_{b'+1})
+// and  total = T_0 + r_0 (T_1 + r_1 (T_2 + ...)),  T_L = sum_q t_q at level L.  The radix of a level is chosen to
+// keep about 2^17 threads busy (the serial depth of a level is 2 r additions), the last few thousand elements are
+// finished by the direct kernel (weight q applied by double-and-add, log depth).
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t RED_CHUNK = 16;
 
-// level 0 reads the (collapsed) accumulate output through segoff; higher levels read a dense array whose
-// element 0 carries weight 0 and is skipped (shift = 1).
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce_level_kernel(const G1XYZZ* __restrict__ in,
-                                                                       const uint32_t* __restrict__ segoff,
-                                                                       uint32_t n_in, uint32_t in_stride, uint32_t shift,
-                                                                       G1XYZZ* __restrict__ out_u, uint32_t n_out,
-                                                                       G1XYZZ* __restrict__ level_partials) {
-    __shared__ G1XYZZ sh[RED_THREADS];
+// level 0 reads the accumulate output through pbase (summing the <= HEAVY_PARTS partials of a bucket); higher
+// levels read a dense array whose element 0 carries weight 0 and is skipped (shift = 1).  No block-level sum here:
+// the per-thread t_q are written out and msm_reduce_gather adds them all in one go (a tree sum per level would
+// put 7 more serial additions on the critical path of every level).
+__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_level_kernel(const G1XYZZ* __restrict__ in,
+                                                                          const uint32_t* __restrict__ pbase,
+                                                                          uint32_t n_in, uint32_t in_stride, uint32_t shift,
+                                                                          uint32_t radix, G1XYZZ* __restrict__ out_u,
+                                                                          uint32_t n_out, G1XYZZ* __restrict__ out_t) {
     const uint32_t set = blockIdx.y;
     const uint32_t q = blockIdx.x * RED_THREADS + threadIdx.x;
-    G1XYZZ tot = xyzz_inf();
-    if (q < n_out) {
-        const uint32_t lo = q * RED_CHUNK;
-        const uint32_t hi = min(lo + RED_CHUNK, n_in);
-        G1XYZZ run = xyzz_inf();
-        for (uint32_t b = hi; b-- > lo;) {
-            G1XYZZ s;
-            if (segoff) {
-                const uint32_t key = set * in_stride + b;
-                const uint32_t a = segoff[key], nparts = segoff[key + 1] - a;
-                s = nparts == 0 ? xyzz_inf() : load_xyzz(in + a);
-                if (nparts > 1 && nparts <= HEAVY_PARTS) {
-                    for (uint32_t j = 1; j < nparts; j++) {
-                        G1XYZZ o = load_xyzz(in + a + j);
-                        xyzz_add(s, o);
-                    }
-                }
-            } else {
-                s = load_xyzz(in + (size_t)set * in_stride + b + shift);
+    if (q >= n_out) return;
+    const uint32_t lo = q * radix;
+    const uint32_t hi = min(lo + radix, n_in);
+    G1XYZZ run = xyzz_inf(), tot = xyzz_inf();
+    for (uint32_t b = hi; b-- > lo;) {
+        if (pbase) {
+            const uint32_t key = set * in_stride + b;
+            const uint32_t a = pbase[key];
+            uint32_t nparts = pbase[key + 1] - a;
+            if (nparts > HEAVY_PARTS) nparts = 1;  // collapsed into the first slot
+            for (uint32_t j = 0; j < nparts; j++) {
+                G1XYZZ o = load_xyzz(in + a + j);
+                xyzz_add(run, o);
             }
-            xyzz_add(run, s);
-            xyzz_add(tot, run);
+        } else {
+            G1XYZZ o = load_xyzz(in + (size_t)set * in_stride + b + shift);
+            xyzz_add(run, o);
         }
-        store_xyzz(out_u + (size_t)set * n_out + q, run);
+        xyzz_add(tot, run);
     }
-    block_tree_sum(tot, sh);
-    if (threadIdx.x == 0) store_xyzz(level_partials + (size_t)set * gridDim.x + blockIdx.x, tot);
+    store_xyzz(out_u + (size_t)set * n_out + q, run);
+    store_xyzz(out_t + (size_t)set * n_out + q, tot);
 }
 
-// Tail of the hierarchy: once few elements are left, every thread scales its element by its weight q
-// (double-and-add, <= 15 bits) and the block tree-sums them -- log depth instead of more serial levels.
-constexpr uint32_t RED_DIRECT_MAX = 32768;
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce_direct_kernel(const G1XYZZ* __restrict__ in, uint32_t n_in,
-                                                                        G1XYZZ* __restrict__ direct_partials) {
-    __shared__ G1XYZZ sh[RED_THREADS];
+// Tail of the hierarchy: every thread scales its element by its weight q (double-and-add, <= 12 bits).
+constexpr uint32_t RED_DIRECT_MAX = 4096;
+__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_direct_kernel(const G1XYZZ* __restrict__ in, uint32_t n_in,
+                                                                           G1XYZZ* __restrict__ out_t) {
     const uint32_t set = blockIdx.y;
     const uint32_t q = blockIdx.x * RED_THREADS + threadIdx.x;
+    if (q >= n_in) return;
     G1XYZZ v = xyzz_inf();
-    if (q >= 1 && q < n_in) v = xyzz_mul_small(load_xyzz(in + (size_t)set * n_in + q), q);
-    block_tree_sum(v, sh);
-    if (threadIdx.x == 0) store_xyzz(direct_partials + (size_t)set * gridDim.x + blockIdx.x, v);
+    if (q >= 1) v = xyzz_mul_small(load_xyzz(in + (size_t)set * n_in + q), q);
+    store_xyzz(out_t + (size_t)set * n_in + q, v);
 }
 
+constexpr int RED_MAX_LEVELS = 12;
 struct RedLevels {
     uint32_t nlevels;
-    uint32_t blocks[8];   // block partials per set at each level
-    uint32_t offset[8];   // start of the level inside level_partials (in units of G1XYZZ, per-set blocks contiguous)
-    uint32_t direct_blocks, direct_offset;  // partials of the direct tail (0 blocks: none)
+    uint32_t count[RED_MAX_LEVELS];       // t values per set at each level
+    uint32_t offset[RED_MAX_LEVELS];      // start of the level inside the t array (per-set runs contiguous)
+    uint32_t log_radix[RED_MAX_LEVELS];
+    uint32_t direct_count, direct_offset;  // values of the direct tail (0: none)
 };
 
-// grid = nsets: Horner over the levels, 4 doublings (x16) per level
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce_final_kernel(const G1XYZZ* __restrict__ level_partials,
-                                                                       RedLevels lv, G1XYZZ* __restrict__ set_sums) {
+// grid = (G, nsets).  Every thread folds its strided share of each level's t values while running the Horner
+// recurrence over the levels ON ITS OWN share (the recurrence is linear, so the sum over all threads of the
+// per-thread results is the result); one tree sum per block.  With G == 1 the block's sum is the set's sum.
+__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_gather_kernel(const G1XYZZ* __restrict__ tvals, RedLevels lv,
+                                                                           uint32_t nsets, G1XYZZ* __restrict__ out) {
+    __shared__ G1XYZZ sh[RED_THREADS];
+    const uint32_t set = blockIdx.y;
+    const uint32_t g = blockIdx.x * RED_THREADS + threadIdx.x, stride = gridDim.x * RED_THREADS;
+    G1XYZZ acc = xyzz_inf();
+    if (lv.direct_count) {
+        const G1XYZZ* base = tvals + lv.direct_offset + (size_t)set * lv.direct_count;
+        for (uint32_t j = g; j < lv.direct_count; j += stride) {
+            G1XYZZ o = load_xyzz(base + j);
+            xyzz_add(acc, o);
+        }
+    }
+    for (int L = (int)lv.nlevels - 1; L >= 0; L--) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < lv.log_radix[L]; k++) acc = xyzz_dbl(acc);
+        const G1XYZZ* base = tvals + lv.offset[L] + (size_t)set * lv.count[L];
+        for (uint32_t j = g; j < lv.count[L]; j += stride) {
+            G1XYZZ o = load_xyzz(base + j);
+            xyzz_add(acc, o);
+        }
+    }
+    block_tree_sum(acc, sh);
+    if (threadIdx.x == 0) store_xyzz(out + (size_t)set * gridDim.x + blockIdx.x, acc);
+}
+
+// grid = nsets: sum of the `count` per-block results of the gather
+__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_final_kernel(const G1XYZZ* __restrict__ parts, uint32_t count,
+                                                                          G1XYZZ* __restrict__ set_sums) {
     __shared__ G1XYZZ sh[RED_THREADS];
     const uint32_t set = blockIdx.x;
     G1XYZZ acc = xyzz_inf();
-    if (lv.direct_blocks) {
-        G1XYZZ v = xyzz_inf();
-        const G1XYZZ* base = level_partials + lv.direct_offset + (size_t)set * lv.direct_blocks;
-        for (uint32_t j = threadIdx.x; j < lv.direct_blocks; j += RED_THREADS) {
-            G1XYZZ o = load_xyzz(base + j);
-            xyzz_add(v, o);
-        }
-        block_tree_sum(v, sh);
-        if (threadIdx.x == 0) acc = v;
+    for (uint32_t j = threadIdx.x; j < count; j += RED_THREADS) {
+        G1XYZZ o = load_xyzz(parts + (size_t)set * count + j);
+        xyzz_add(acc, o);
     }
-    for (int L = (int)lv.nlevels - 1; L >= 0; L--) {
-        G1XYZZ v = xyzz_inf();
-        const G1XYZZ* base = level_partials + lv.offset[L] + (size_t)set * lv.blocks[L];
-        for (uint32_t j = threadIdx.x; j < lv.blocks[L]; j += RED_THREADS) {
-            G1XYZZ o = load_xyzz(base + j);
-            xyzz_add(v, o);
-        }
-        block_tree_sum(v, sh);
-        if (threadIdx.x == 0) {
-#pragma unroll 1
-            for (int k = 0; k < 4; k++) acc = xyzz_dbl(acc);
-            xyzz_add(acc, v);
-        }
-    }
+    block_tree_sum(acc, sh);
     if (threadIdx.x == 0) store_xyzz(set_sums + set, acc);
 }
 
@@ -582,10 +591,13 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const uint32_t nkeys = g.nsets * g.nbuckets;
     const uint64_t max_entries = n * g.nwin;
     if (max_entries >= (1ull << 32)) return set_err(ctx, KZG_ERR_ARG, "msm: n * windows exceeds 2^32 entries");
-    // slice length: about one average bucket, clamped to [16, 128] entries per accumulate thread
-    uint64_t slice = max_entries / nkeys + 1;
+    // slice length: a few average buckets (every slice start costs one extra partial sum), but short enough to
+    // give every SM several waves of equal-sized tasks
+    uint64_t slice = 4 * (max_entries / nkeys + 1);
+    const uint64_t waves = (uint64_t)ctx->sm_count * 512 * 4;
+    if (slice > max_entries / waves) slice = max_entries / waves;
     if (slice < 16) slice = 16;
-    if (slice > 128) slice = 128;
+    if (slice > 512) slice = 512;
     g.seg = (uint32_t)slice;
     const uint64_t max_tasks = (max_entries + slice - 1) / slice;
     const uint64_t max_parts = max_tasks + nkeys + 1;
@@ -593,32 +605,39 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     // reduction hierarchy
     RedLevels lv;
     memset(&lv, 0, sizeof(lv));
-    uint32_t n_in[8], n_out[8];
-    uint32_t part_total = 0;
+    uint32_t n_in[RED_MAX_LEVELS], n_out[RED_MAX_LEVELS];
+    uint32_t t_total = 0;   // per-thread t values over all levels and sets
     size_t u_total = 0;
-    uint32_t direct_n = 0;  // elements handed to the direct tail (index = weight)
     {
         uint32_t cur = g.nbuckets;  // weighted elements at this level
         while (true) {
             const uint32_t L = lv.nlevels;
+            // radix 4..16: keep ~2^17 threads per level across the sets
+            uint32_t lr = 2;
+            while (lr < 4 && ((uint64_t)cur * g.nsets >> (lr + 1)) >= (1u << 17)) lr++;
             n_in[L] = cur;
-            n_out[L] = (cur + RED_CHUNK - 1) / RED_CHUNK;
-            lv.blocks[L] = (n_out[L] + RED_THREADS - 1) / RED_THREADS;
-            lv.offset[L] = part_total;
-            part_total += lv.blocks[L] * g.nsets;
+            n_out[L] = (cur + (1u << lr) - 1) >> lr;
+            lv.log_radix[L] = lr;
+            lv.count[L] = n_out[L];
+            lv.offset[L] = t_total;
+            t_total += n_out[L] * g.nsets;
             u_total += (size_t)n_out[L] * g.nsets;
             lv.nlevels++;
             if (n_out[L] <= 1) break;
-            if (n_out[L] <= RED_DIRECT_MAX || lv.nlevels == 8) {
-                direct_n = n_out[L];
-                lv.direct_blocks = (direct_n + RED_THREADS - 1) / RED_THREADS;
-                lv.direct_offset = part_total;
-                part_total += lv.direct_blocks * g.nsets;
+            if (n_out[L] <= RED_DIRECT_MAX || lv.nlevels == RED_MAX_LEVELS) {
+                lv.direct_count = n_out[L];
+                lv.direct_offset = t_total;
+                t_total += lv.direct_count * g.nsets;
                 break;
             }
             cur = n_out[L] - 1;  // element 0 of the next level has weight 0
         }
     }
+    // gather blocks per set: ~8 values per thread, at most 256 blocks
+    uint32_t gather_blocks = (t_total / g.nsets + RED_THREADS * 8 - 1) / (RED_THREADS * 8);
+    if (gather_blocks < 1) gather_blocks = 1;
+    if (gather_blocks > 256) gather_blocks = 256;
+    const uint32_t part_total = gather_blocks * g.nsets;
 
     // scratch layout
     size_t off = 0;
@@ -629,6 +648,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const size_t o_sorted = off;   off = align_up(off + sizeof(uint32_t) * max_entries, 256);
     const size_t o_partials = off; off = align_up(off + sizeof(G1XYZZ) * max_parts, 256);
     const size_t o_u = off;        off = align_up(off + sizeof(G1XYZZ) * u_total, 256);
+    const size_t o_tv = off;       off = align_up(off + sizeof(G1XYZZ) * t_total, 256);
     const size_t o_lp = off;       off = align_up(off + sizeof(G1XYZZ) * part_total, 256);
     const size_t o_sets = off;     off = align_up(off + sizeof(G1XYZZ) * g.nsets, 256);
     const uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
@@ -644,7 +664,8 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     uint32_t* sorted = (uint32_t*)(sc + o_sorted);
     G1XYZZ* partials = (G1XYZZ*)(sc + o_partials);
     G1XYZZ* u_arrays = (G1XYZZ*)(sc + o_u);
-    G1XYZZ* level_partials = (G1XYZZ*)(sc + o_lp);
+    G1XYZZ* tvals = (G1XYZZ*)(sc + o_tv);
+    G1XYZZ* gather_parts = (G1XYZZ*)(sc + o_lp);
     G1XYZZ* set_sums = (G1XYZZ*)(sc + o_sets);
     uint32_t* tile_sums = (uint32_t*)(sc + o_tiles);
     uint32_t* heavy = (uint32_t*)(sc + o_heavy);  // [0] = count, [1..] = keys
@@ -672,22 +693,27 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         const G1XYZZ* in = partials;
         G1XYZZ* u = u_arrays;
         for (uint32_t L = 0; L < lv.nlevels; L++) {
-            KZG_LAUNCH(ctx, msm_reduce_level_kernel, dim3(lv.blocks[L], g.nsets), RED_THREADS, 0, in,
-                       L == 0 ? segoff : nullptr, n_in[L], L == 0 ? g.nbuckets : n_out[L - 1], L == 0 ? 0u : 1u, u, n_out[L],
-                       level_partials + lv.offset[L]);
+            const uint32_t blocks = (n_out[L] + RED_THREADS - 1) / RED_THREADS;
+            KZG_LAUNCH(ctx, msm_reduce_level_kernel, dim3(blocks, g.nsets), RED_THREADS, 0, in, L == 0 ? segoff : nullptr,
+                       n_in[L], L == 0 ? g.nbuckets : n_out[L - 1], L == 0 ? 0u : 1u, 1u << lv.log_radix[L], u, n_out[L],
+                       tvals + lv.offset[L]);
             in = u;
             u += (size_t)n_out[L] * g.nsets;
         }
-        if (lv.direct_blocks)
-            KZG_LAUNCH(ctx, msm_reduce_direct_kernel, dim3(lv.direct_blocks, g.nsets), RED_THREADS, 0, in, direct_n,
-                       level_partials + lv.direct_offset);
+        if (lv.direct_count) {
+            const uint32_t blocks = (lv.direct_count + RED_THREADS - 1) / RED_THREADS;
+            KZG_LAUNCH(ctx, msm_reduce_direct_kernel, dim3(blocks, g.nsets), RED_THREADS, 0, in, lv.direct_count,
+                       tvals + lv.direct_offset);
+        }
     }
-    if (g.nsets == 1) {
-        KZG_LAUNCH(ctx, msm_reduce_final_kernel, 1, RED_THREADS, 0, level_partials, lv, result_dev);
+    G1XYZZ* sums_out = g.nsets == 1 ? result_dev : set_sums;
+    if (gather_blocks == 1) {
+        KZG_LAUNCH(ctx, msm_reduce_gather_kernel, dim3(1, g.nsets), RED_THREADS, 0, tvals, lv, g.nsets, sums_out);
     } else {
-        KZG_LAUNCH(ctx, msm_reduce_final_kernel, g.nsets, RED_THREADS, 0, level_partials, lv, set_sums);
-        KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, result_dev);
+        KZG_LAUNCH(ctx, msm_reduce_gather_kernel, dim3(gather_blocks, g.nsets), RED_THREADS, 0, tvals, lv, g.nsets, gather_parts);
+        KZG_LAUNCH(ctx, msm_reduce_final_kernel, g.nsets, RED_THREADS, 0, gather_parts, gather_blocks, sums_out);
     }
+    if (g.nsets > 1) KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, result_dev);
     KZG_CHECK_LAUNCH(ctx);
     return KZG_OK;
 }
