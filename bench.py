@@ -177,7 +177,10 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream made current for the whole run: the library launches on it (a NULL stream
+    # pointer would make kzg_ctx_create open a private stream that torch's events do not see)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     curve = Curve(local_rank, stream.cuda_stream)     # kernels go on torch's current stream: torch events see them
     curve_mod._CURVES[local_rank] = curve             # the drop-in provers pick this curve up (getCurveFromName cache)
     lib, ctx = curve.lib, curve.ctx

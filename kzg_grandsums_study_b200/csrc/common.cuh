@@ -25,6 +25,12 @@ struct kzg_ctx {
     kzg::Fr* tw_lo[2] = {nullptr, nullptr};
     kzg::Fr* tw_hi[2] = {nullptr, nullptr};
     bool ntt_attr_set = false;
+    // data-independent coset tables of the fused provers, keyed by (log2 m): 1 / (n (x_i - 1)) on g H_m (prover.cu)
+    struct CosetTable {
+        uint64_t n = 0, m = 0;
+        kzg::Fr* inv_nx = nullptr;
+    };
+    std::vector<CosetTable> coset_tables;
     // persistent scratch (grown on demand)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

@@ -266,6 +266,7 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
             cudaEventDestroy(pr.second);
         }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    for (auto& t : ctx->coset_tables) cudaFree(t.inv_nx);
     cudaFree(ctx->scratch);
     cudaFree(ctx->dev_small);
     cudaFreeHost(ctx->pinned);

@@ -67,9 +67,16 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
     const uint32_t lane = threadIdx.x & 31;
     Fr s = fp_zero<FrP>();  // lanes past the end run the loop with a zero scalar: the warp stays converged
     if (i < n) {
-        s = fp_load<FrP>(scalars + i);
+        // streaming read (evict-first): the scalars are read once and must not push the bucket cursors and the
+        // partially written sectors of `sorted` out of L2
+        const uint4* q = reinterpret_cast<const uint4*>(scalars + i);
+        uint4 a = __ldcs(q), b = __ldcs(q + 1);
+        s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
+        s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
         if (montgomery) s = fp_from_mont(s);
     }
+    uint64_t keep_policy = 0;
+    if (SCATTER) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
     uint32_t carry = 0;
     const uint32_t half = g.nbuckets;  // 2^(c-1)
     const bool table = g.nsets == 1;
@@ -96,7 +103,11 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
             base = __shfl_sync(0xffffffffu, base, leader);
             if (valid) {
                 uint32_t entry = table ? (uint32_t)(w * g.stride + i) : (uint32_t)i;
-                sorted[base + rank] = entry | (neg << 31);
+                // every bucket has ONE partially filled 32-byte sector of `sorted` at any time (2^(c-1) x 32 B in
+                // total): ask L2 to keep those lines until their other 7 entries arrive
+                asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(sorted + base + rank), "r"(entry | (neg << 31)),
+                             "l"(keep_policy)
+                             : "memory");
             }
         }
     }

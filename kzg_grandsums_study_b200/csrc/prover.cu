@@ -227,15 +227,33 @@ int kzg_prover_create(kzg_ctx* ctx, kzg_srs* srs, int kind, uint32_t n_bits, uin
     if (r == KZG_OK) r = dev_alloc(p, n, &p->ev_acc);
     if (r == KZG_OK) r = dev_alloc(p, n, &p->co_acc);
     if (r == KZG_OK) r = dev_alloc(p, p->m, &p->co_q);
-    if (r == KZG_OK) r = dev_alloc(p, p->m, &p->inv_nx);
     if (r == KZG_OK) {
-        // data-independent coset table: 1 / (n (x_i - 1)),  x_i = g w_m^i,  g = w_{2m}
-        const uint32_t step = 1u << (NTT_MAX_LOG - (log2u(p->m) + 1));
-        KZG_LAUNCH(ctx, coset_xm1_kernel, grid_for(p->m, PR_THREADS), PR_THREADS, 0, p->inv_nx, p->m, step, h_from_u64(n),
-                   ctx->tw_lo[0], ctx->tw_hi[0]);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, cudaGetErrorString(e));
-        if (r == KZG_OK) r = fr_batch_inverse(ctx, p->inv_nx, p->inv_nx, p->m);
+        // data-independent coset table: 1 / (n (x_i - 1)),  x_i = g w_m^i,  g = w_{2m}; built once per (n, m)
+        for (auto& t : ctx->coset_tables)
+            if (t.n == n && t.m == p->m) p->inv_nx = t.inv_nx;
+        if (!p->inv_nx) {
+            Fr* tab = nullptr;
+            cudaError_t e = cudaMalloc((void**)&tab, sizeof(Fr) * p->m);
+            if (e != cudaSuccess) r = set_err(ctx, KZG_ERR_NOMEM, std::string("coset table allocation failed: ") + cudaGetErrorString(e));
+            if (r == KZG_OK) {
+                const uint32_t step = 1u << (NTT_MAX_LOG - (log2u(p->m) + 1));
+                KZG_LAUNCH(ctx, coset_xm1_kernel, grid_for(p->m, PR_THREADS), PR_THREADS, 0, tab, p->m, step, h_from_u64(n),
+                           ctx->tw_lo[0], ctx->tw_hi[0]);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, cudaGetErrorString(e));
+            }
+            if (r == KZG_OK) r = fr_batch_inverse(ctx, tab, tab, p->m);
+            if (r == KZG_OK) {
+                kzg_ctx::CosetTable t;
+                t.n = n;
+                t.m = p->m;
+                t.inv_nx = tab;
+                ctx->coset_tables.push_back(t);
+                p->inv_nx = tab;
+            } else if (tab) {
+                cudaFree(tab);
+            }
+        }
     }
     if (r != KZG_OK) {
         kzg_prover_destroy(p);

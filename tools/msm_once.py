@@ -15,7 +15,9 @@ log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 window = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 n = 1 << log_n
-curve = Curve(0, torch.cuda.current_stream().cuda_stream)
+_stream = torch.cuda.Stream()
+torch.cuda.set_stream(_stream)
+curve = Curve(0, _stream.cuda_stream)
 lib, ctx = curve.lib, curve.ctx
 tau = synthetic.tau_from_seed(1001)
 srs = C.c_void_p()

@@ -1,0 +1,79 @@
+"""Turn ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+  python tools/summarize_profiles.py launches <csv> <out.md> <title> [last_n]
+  python tools/summarize_profiles.py full <ncu-rep> <out.md> <title>
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+
+def launches(path, out, title, last_n=None):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5 and r[0].isdigit()]
+    if last_n:
+        rows = rows[-int(last_n):]
+    agg = collections.OrderedDict()
+    total = 0.0
+    for r in rows:
+        name = r[4].split("(")[0].replace("void ", "").strip()
+        t = float(r[-1]) / 1e6
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+        total += t
+    with open(out, "w") as f:
+        f.write("# %s\n\n" % title)
+        f.write("Source: `ncu --metrics gpu__time_duration.sum --clock-control none` (per-launch times are cold-cache and "
+                "serialised: compare SHARES, not absolutes).  %d launches, %.3f ms in total.\n\n" % (len(rows), total))
+        f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
+        for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write("| `%s` | %d | %.3f | %.1f %% |\n" % (k, v[0], v[1], 100 * v[1] / total))
+        f.write("\nLaunch order (last sequence):\n\n```\n")
+        for r in rows:
+            f.write("%-64s %10.3f ms\n" % (r[4][:64], float(r[-1]) / 1e6))
+        f.write("```\n")
+
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__inst_executed.sum", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+]
+
+
+def full(path, out, title):
+    p = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    rows = list(csv.reader(p.stdout.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        f.write("# %s\n\nSource: `ncu --set full --clock-control none --import-source on` (`%s`).\n\n" % (title, path))
+        for val in rows[2:]:
+            name = val[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+            f.write("## `%s`\n\n| metric | unit | value |\n|---|---|---:|\n" % name.split("(")[0])
+            for h, u, v in zip(hdr, units, val):
+                if h in WANT:
+                    f.write("| `%s` | %s | %s |\n" % (h, u, v))
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(*sys.argv[2:])
+    else:
+        full(*sys.argv[2:])
