@@ -13,8 +13,8 @@ from .ptau_utils import readPTauHeader
 
 
 def _host_column(ev):
-    """bytes of an Evaluations column as handed in by the caller (host buffer)"""
-    return ev.tobytes()
+    """an Evaluations column as handed in by the caller, zero-copy when it already is a host buffer"""
+    return ev.host_buffer()
 
 
 def prove(kind, pTauFilename, evalsFs, evalsTs, evalsSelF=None, evalsSelT=None, device=0, logger=None, trace=None):

@@ -50,14 +50,41 @@ class Evaluations:
 
     # ---- accessors ----------------------------------------------------------------------------------
     def tobytes(self):
-        return self.eval.tobytes() if isinstance(self.eval, DeviceBuffer) else bytes(self.eval)
+        if isinstance(self.eval, DeviceBuffer):
+            return self.eval.tobytes()
+        if isinstance(self.eval, (bytes, bytearray)):
+            return bytes(self.eval)
+        if hasattr(self.eval, "data_ptr"):          # torch tensor (e.g. pinned host memory)
+            return self.eval.cpu().numpy().tobytes()
+        return memoryview(self.eval).tobytes()       # numpy array or any buffer
+
+    def host_buffer(self):
+        """the evaluations as something as_ptr() can hand to the C ABI WITHOUT copying when they already sit in
+        host memory (bytes, bytearray, numpy array, pinned torch tensor); device buffers are downloaded"""
+        if isinstance(self.eval, DeviceBuffer):
+            return self.eval.tobytes()
+        if isinstance(self.eval, memoryview):
+            return self.eval.tobytes()
+        return self.eval
+
+    def _nbytes(self):
+        e = self.eval
+        if isinstance(e, DeviceBuffer):
+            return e.byteLength
+        if isinstance(e, (bytes, bytearray)):
+            return len(e)
+        if hasattr(e, "data_ptr"):
+            return e.numel() * e.element_size()
+        return memoryview(e).nbytes
 
     def getEvaluation(self, index):                             # evaluations.js:68-74
         if (index + 1) * 32 > self.length() * 32:
             raise IndexError("Evaluations.getEvaluation() out of bounds")
         if isinstance(self.eval, DeviceBuffer):
             return self.eval.slice(index * 32, (index + 1) * 32)
-        return bytes(self.eval[index * 32:(index + 1) * 32])
+        if isinstance(self.eval, (bytes, bytearray)):
+            return bytes(self.eval[index * 32:(index + 1) * 32])
+        return self.tobytes()[index * 32:(index + 1) * 32]
 
     def getEvaluationSequence(self, start, end):                # evaluations.js:76-88
         if start > end:
@@ -68,7 +95,9 @@ class Evaluations:
             raise IndexError("Evaluations.getEvaluationSequence() end index is out of bounds")
         if isinstance(self.eval, DeviceBuffer):
             return self.eval.slice(start * 32, end * 32)
-        return bytes(self.eval[start * 32:end * 32])
+        if isinstance(self.eval, (bytes, bytearray)):
+            return bytes(self.eval[start * 32:end * 32])
+        return self.tobytes()[start * 32:end * 32]
 
     def setEvaluation(self, index, value):                      # evaluations.js:90-96
         if index > self.length() - 1:
@@ -76,12 +105,12 @@ class Evaluations:
         if isinstance(self.eval, DeviceBuffer):
             self.curve.check(self.curve.lib.kzg_buf_upload(self.curve.ctx, self.eval.handle, index, as_ptr(bytes(value)), 1))
         else:
-            b = bytearray(self.eval)
+            b = bytearray(self.tobytes())
             b[index * 32:(index + 1) * 32] = bytes(value)
             self.eval = b
 
     def length(self):                                           # evaluations.js:99-108
-        nbytes = self.eval.byteLength if isinstance(self.eval, DeviceBuffer) else len(self.eval)
+        nbytes = self._nbytes()
         if nbytes % 32:
             raise ValueError("Polynomial evaluations buffer has incorrect size")
         return nbytes // 32
@@ -96,7 +125,7 @@ class Evaluations:
             out = C.c_int()
             self.curve.check(self.curve.lib.kzg_buf_all_equal(self.curve.ctx, self.eval.handle, as_ptr(value), C.byref(out)))
             return bool(out.value)
-        return bytes(self.eval) == value * self.length()
+        return self.tobytes() == value * self.length()
 
     def isAllZeros(self):                                       # evaluations.js:118-121
         return self._all_equal(self.Fr.zero)

@@ -181,3 +181,25 @@ def test_config_c3_selected_vector(nbits, curve, tau, ptau_factory):
     got, want, tr, otr = run_both("gs", curve, tau, ptau_factory, seed=3, nbits=nbits, k=4, selected=True)
     assert_same_proof(got, want, tr, otr)
     assert pr.grandsum_verifier(got, nbits, tau=tau)
+
+
+def test_column_buffer_types(curve, tau, ptau_factory):
+    """host columns may be bytes, bytearray, numpy arrays or (pinned) torch tensors -- same proof"""
+    import numpy as np
+    import torch
+    from kzg_grandsums_study_b200.grandsum import mset_eq_kzg_grandsum_prover
+    from kzg_grandsums_study_b200.polynomial import Evaluations
+    nbits = 6
+    f = inputs.random_column(5, 1 << nbits)
+    fb, tb = bn.fr_vec_to_std_bytes(f), bn.fr_vec_to_std_bytes(inputs.rotate_right(f))
+    path = ptau_factory(nbits)
+    ref = pr.proof_bytes(mset_eq_kzg_grandsum_prover(path, Evaluations(fb, curve), Evaluations(tb, curve)))
+    variants = [
+        (bytearray(fb), bytearray(tb)),
+        (np.frombuffer(fb, dtype=np.uint64).reshape(-1, 4).copy(), np.frombuffer(tb, dtype=np.uint8).copy()),
+        (torch.frombuffer(bytearray(fb), dtype=torch.uint8).pin_memory(), torch.frombuffer(bytearray(tb), dtype=torch.uint8).pin_memory()),
+    ]
+    for a, b in variants:
+        ea, eb = Evaluations(a, curve), Evaluations(b, curve)
+        assert ea.length() == 1 << nbits and ea.getEvaluation(3) == fb[96:128]
+        assert pr.proof_bytes(mset_eq_kzg_grandsum_prover(path, ea, eb)) == ref

@@ -24,7 +24,9 @@ lib, ctx = curve.lib, curve.ctx
 tau = synthetic.tau_from_seed(1001)
 f = synthetic.random_fr_std(4, n)
 t = f[synthetic.permutation(4, n)]
-fb, tb = f.tobytes(), t.tobytes()
+import numpy as np  # noqa: E402
+fb = torch.from_numpy(f.view(np.uint8).reshape(-1).copy()).pin_memory()
+tb = torch.from_numpy(np.ascontiguousarray(t).view(np.uint8).reshape(-1).copy()).pin_memory()
 prover = mset_eq_kzg_grandsum_prover if kind == "gs" else mset_eq_kzg_grandproduct_prover
 
 # per-call timing of the C ABI rounds
