@@ -195,11 +195,35 @@ class _G1:
         return bytes(jac[:64])
 
 
-class Curve:
+class HostCurve:
+    """the host-only part of the curve object (Fr / G1 byte helpers, Keccak): what the verifiers and the transcript
+    need.  No device, no context."""
     name = "bn128"
     q = Q
     r = R
 
+    def __init__(self):
+        self.lib = _lib.load()
+        self.ctx = None
+        self.Fr = _Fr(self)
+        self.G1 = _G1(self)
+        self.F1 = _F1()
+
+    def terminate(self):
+        pass
+
+
+_HOST_CURVE = None
+
+
+def getHostCurve():
+    global _HOST_CURVE
+    if _HOST_CURVE is None:
+        _HOST_CURVE = HostCurve()
+    return _HOST_CURVE
+
+
+class Curve(HostCurve):
     def __init__(self, device=0, stream=None):
         self.lib = _lib.load()
         h = C.c_void_p()

@@ -49,7 +49,16 @@ def run_both(kind, curve, tau, ptau_factory, seed, nbits, k=1, selected=False, r
     got = gpu_prover(path, fs, ts, dev_args[2], dev_args[3], trace=trace)
     otrace = {}
     want = cpu_prover(pr.TrapdoorSrs(tau, power), std[0], std[1], sels[0], sels[1], trace=otrace)
+    run_both.last_path = path
     return got, want, trace, otrace
+
+
+def package_verify(kind, proof, nbits):
+    """the drop-in verifier of the package (host code, real pairing against [tau]_2 of the same .ptau)"""
+    from kzg_grandsums_study_b200.grandsum import mset_eq_kzg_grandsum_verifier
+    from kzg_grandsums_study_b200.grandproduct import mset_eq_kzg_grandproduct_verifier
+    v = mset_eq_kzg_grandsum_verifier if kind == "gs" else mset_eq_kzg_grandproduct_verifier
+    return v(run_both.last_path, proof, nbits)
 
 
 def assert_same_proof(got, want, trace, otrace):
@@ -95,6 +104,7 @@ def test_plain_proofs(kind, nbits, curve, tau, ptau_factory):
     assert_same_proof(got, want, tr, otr)
     verifier = pr.grandsum_verifier if kind == "gs" else pr.grandproduct_verifier
     assert verifier(got, nbits, tau=tau)
+    assert package_verify(kind, got, nbits) is True
 
 
 @pytest.mark.parametrize("kind", ["gs", "gp"])
@@ -106,6 +116,9 @@ def test_vector_and_selected_proofs(kind, nbits, k, selected, curve, tau, ptau_f
     assert_same_proof(got, want, tr, otr)
     verifier = pr.grandsum_verifier if kind == "gs" else pr.grandproduct_verifier
     assert verifier(got, nbits, tau=tau)
+    assert package_verify(kind, got, nbits) is True
+    got["evaluations"][next(iter(got["evaluations"]))] = bn.fr_to_mont_bytes(12345)
+    assert package_verify(kind, got, nbits) is False
 
 
 @pytest.mark.parametrize("kind", ["gs", "gp"])

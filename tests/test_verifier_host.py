@@ -1,0 +1,66 @@
+"""CPU: the drop-in verifiers (host code with a real optimal-ate pairing) accept the oracle's honest proofs and reject
+tampered ones, in agreement with the oracle's trapdoor check -- the property the reference's tests assert
+(test/mset_eq_kzg_grandsum.test.js:24-104: prove, verify, assert.ok(isValid))."""
+import pytest
+
+from oracle.py import bn254 as bn, inputs, protocol as pr, ptau as opt
+
+
+def test_pairing_bilinear(lib_path):
+    from kzg_grandsums_study_b200 import host_bn254 as hb
+    e1 = hb.pairing(hb.G2_GEN, hb.G1_GEN)
+    assert e1 != hb._F12_ONE and hb.f12_pow(e1, hb.R) == hb._F12_ONE
+    assert hb.pairing(hb.G2_GEN, hb.g1_mul(hb.G1_GEN, 3)) == hb.f12_pow(e1, 3)
+    assert hb.pairing(bn.g2_mul(bn.G2_GEN, 5), hb.G1_GEN) == hb.f12_pow(e1, 5)
+    tau, a = 123456789, 987654321
+    A = hb.g1_neg(hb.g1_mul(hb.G1_GEN, a))
+    B = hb.g1_mul(hb.G1_GEN, a * tau % hb.R)
+    assert hb.pairing_eq(A, bn.g2_mul(bn.G2_GEN, tau), B, hb.G2_GEN)
+    assert not hb.pairing_eq(A, bn.g2_mul(bn.G2_GEN, tau + 1), B, hb.G2_GEN)
+    # host G1 arithmetic against the oracle
+    for k in (1, 2, 7, bn.R - 1, 1 << 200):
+        assert hb.g1_mul(hb.G1_GEN, k) == bn.g1_mul((1, 2), k)
+
+
+@pytest.mark.parametrize("kind", ["gs", "gp"])
+@pytest.mark.parametrize("k,selected", [(1, False), (3, False), (1, True), (2, True)])
+def test_verifiers_accept_and_reject(kind, k, selected, tmp_path, lib_path):
+    from kzg_grandsums_study_b200.grandsum import mset_eq_kzg_grandsum_verifier
+    from kzg_grandsums_study_b200.grandproduct import mset_eq_kzg_grandproduct_verifier
+    nbits = 3
+    n = 1 << nbits
+    tau = inputs.tau_from_seed(4242)
+    path = str(tmp_path / "v.ptau")
+    opt.write_ptau(path, nbits, tau)
+    cols_f = [inputs.random_column(10 + i, n) for i in range(k)]
+    cols_t = [inputs.rotate_right(c) for c in cols_f]
+    sel_f = sel_t = None
+    if selected:
+        one, zero = bn.fr_to_mont_bytes(1), bytes(32)
+        sel_f, sel_t = one * (n - 1) + zero, zero + one * (n - 1)
+    prover = pr.grandsum_prover if kind == "gs" else pr.grandproduct_prover
+    oracle_verifier = pr.grandsum_verifier if kind == "gs" else pr.grandproduct_verifier
+    verifier = mset_eq_kzg_grandsum_verifier if kind == "gs" else mset_eq_kzg_grandproduct_verifier
+    proof = prover(pr.Srs(path, 2 * n), [bn.fr_vec_to_std_bytes(c) for c in cols_f],
+                   [bn.fr_vec_to_std_bytes(c) for c in cols_t], sel_f, sel_t)
+    assert verifier(path, proof, nbits) is True
+    assert oracle_verifier(proof, nbits, tau=tau)
+    # tamper with an evaluation, then with a commitment
+    key = next(iter(proof["evaluations"]))
+    good = proof["evaluations"][key]
+    proof["evaluations"][key] = bn.fr_to_mont_bytes((bn.fr_from_mont_bytes(good) + 1) % bn.R)
+    assert verifier(path, proof, nbits) is False
+    proof["evaluations"][key] = good
+    good_c = proof["commitments"]["Q"]
+    proof["commitments"]["Q"] = bn.g1_to_bytes(bn.g1_mul_gen(5))
+    assert verifier(path, proof, nbits) is False
+    # not a curve point / not a field element: rejected without raising (verifier.js:50,61)
+    proof["commitments"]["Q"] = bn.fq_to_mont_bytes(1) + bn.fq_to_mont_bytes(1)
+    assert verifier(path, proof, nbits) is False
+    proof["commitments"]["Q"] = good_c
+    proof["evaluations"][key] = b"\xff" * 32
+    assert verifier(path, proof, nbits) is False
+    proof["evaluations"][key] = good
+    assert verifier(path, proof, nbits) is True
+    # wrong domain size
+    assert verifier(path, proof, nbits + 1) is False
