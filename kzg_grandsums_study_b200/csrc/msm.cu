@@ -29,6 +29,7 @@
 //   9. g1_finish          sum `count` partial points (count > 1 only for the multi-GPU gather), canonical affine
 // The result is a canonical group element, so it is byte-identical to the reference's regardless of window
 // size, digit signedness, precomputation or summation order.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -98,9 +99,20 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
         const uint32_t leader = __ffs(peers) - 1;
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
         uint32_t base = 0;
+#ifdef KZG_MSM_EXPERIMENT
+        if (SCATTER && g.seg == 0xE1) {  // experiment 1: no returning atomic, pseudo-random store position
+            base = (uint32_t)(((uint64_t)key * 96u + (uint32_t)(i & 63)) % (n * g.nwin));
+        } else
+#endif
         if (valid && lane == leader) base = atomicAdd(&counts_or_cursor[key], (uint32_t)__popc(peers));
         if (SCATTER) {
             base = __shfl_sync(0xffffffffu, base, leader);
+#ifdef KZG_MSM_EXPERIMENT
+            if (g.seg == 0xE2) {  // experiment 2: returning atomic, coalesced store
+                if (valid) sorted[i * g.nwin + w] = base + rank;
+                continue;
+            }
+#endif
             if (valid) {
                 uint32_t entry = table ? (uint32_t)(w * g.stride + i) : (uint32_t)i;
                 // every bucket has ONE partially filled 32-byte sector of `sorted` at any time (2^(c-1) x 32 B in
@@ -555,12 +567,19 @@ static uint32_t auto_window_raw(uint64_t n) {
     return (uint32_t)c;
 }
 
-// table flavour: one bucket set; minimise  n * digits(c) + 3 * 2^(c-1)  (bucket reduction ~ 3 adds per bucket)
+// table flavour: one bucket set.  Cost model in units of one mixed addition:
+//   n * digits(c)                 bucket accumulation
+//   x 1.12 if 2^(c-1) > 2^19      the counting-sort scatter keeps one partially written 128 B line per bucket; beyond
+//                                 ~64 MB of such lines they no longer fit the 126 MB L2 and every 4-byte store becomes a
+//                                 DRAM read-modify-write (measured: 6.3 ms instead of 2.5 ms at 2^24 points)
+//   + 3 * 2^(c-1)                 bucket reduction (~3 full additions per bucket)
 uint32_t msm_table_window(uint64_t n) {
     uint32_t best = 4;
     double best_cost = 1e300;
     for (uint32_t c = 4; c <= 23; c++) {
-        double cost = (double)n * windows_for(c, false) + 3.0 * (double)(1ull << (c - 1));
+        double cost = (double)n * windows_for(c, false);
+        if (c > 20) cost *= 1.12;
+        cost += 3.0 * (double)(1ull << (c - 1));
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
@@ -695,6 +714,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums, segoff, cursor,
                heavy + 1, heavy);
     KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
+
     const uint32_t ablocks = (uint32_t)((max_tasks + 127) / 128);
     timed_begin(ctx, KZG_TIMED_MSM_ACCUMULATE);
     KZG_LAUNCH(ctx, msm_accumulate_kernel, ablocks, 128, 0, pts, sorted, offsets, segoff, nkeys, g.seg, partials);
@@ -725,6 +745,27 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         KZG_LAUNCH(ctx, msm_reduce_final_kernel, g.nsets, RED_THREADS, 0, gather_parts, gather_blocks, sums_out);
     }
     if (g.nsets > 1) KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, result_dev);
+#ifdef KZG_MSM_EXPERIMENT
+    if (getenv("KZG_MSM_EXPERIMENT")) {  // timing experiments on the scatter kernel (results are then discarded)
+        MsmGeom ge = g;
+        cudaEvent_t e0, e1, e2;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        cudaMemcpyAsync(cursor, offsets, sizeof(uint32_t) * nkeys, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaEventRecord(e0, ctx->stream);
+        ge.seg = 0xE1;
+        msm_digits_kernel<true><<<dblocks, 256, 0, ctx->stream>>>(src.scalars, n, src.montgomery, ge, cursor, sorted);
+        cudaEventRecord(e1, ctx->stream);
+        ge.seg = 0xE2;
+        msm_digits_kernel<true><<<dblocks, 256, 0, ctx->stream>>>(src.scalars, n, src.montgomery, ge, cursor, sorted);
+        cudaEventRecord(e2, ctx->stream);
+        cudaEventSynchronize(e2);
+        float t1, t2;
+        cudaEventElapsedTime(&t1, e0, e1);
+        cudaEventElapsedTime(&t2, e1, e2);
+        fprintf(stderr, "[msm experiment] n=%llu: scattered stores without atomics %.3f ms; returning atomics with coalesced stores %.3f ms\n",
+                (unsigned long long)n, t1, t2);
+    }
+#endif
     KZG_CHECK_LAUNCH(ctx);
     return KZG_OK;
 }
