@@ -31,9 +31,17 @@ struct kzg_ctx {
         kzg::Fr* inv_nx = nullptr;
     };
     std::vector<CosetTable> coset_tables;
-    // persistent scratch (grown on demand)
+    // second lane: independent MSMs of one prover round run concurrently (their latency-bound tails overlap the
+    // other one's bucket accumulation).  msm.cu's MsmLane swaps `stream` / the scratch arena for the duration of a
+    // call, so every launch macro keeps using ctx->stream.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int lane = 0;
+    // persistent scratch per lane (grown on demand)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    void* scratch2 = nullptr;
+    size_t scratch2_bytes = 0;
     // pinned host staging for small results
     uint8_t* pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -115,6 +123,13 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
 MsmBases srs_bases(kzg_ctx* ctx, const kzg_srs* srs, uint64_t first);
 int srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t c);
 int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t count, uint8_t out[64]);
+// several independent commitments in one go: MSM i runs on lane (i & 1); one D2H of all the affine results
+struct MsmJob {
+    MsmBases bases;
+    MsmScalarSrc src;
+    uint64_t n;
+};
+int msm_run_batch(kzg_ctx* ctx, const MsmJob* jobs, uint32_t count, uint8_t* out_affine);
 // frops.cu
 int fr_convert(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n, bool to_mont);
 int fr_batch_inverse(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n);

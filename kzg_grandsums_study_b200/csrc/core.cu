@@ -80,24 +80,26 @@ __global__ void __launch_bounds__(256) modmul_peak_kernel(uint32_t iters, uint32
 }
 
 int ctx_scratch(kzg_ctx* ctx, size_t bytes, void** out) {
-    if (bytes > ctx->scratch_bytes) {
-        // stream-ordered free of the old block, then a fresh (larger) one; rounded up to limit regrowth
-        if (ctx->scratch) {
+    void*& arena = ctx->lane == 0 ? ctx->scratch : ctx->scratch2;
+    size_t& arena_bytes = ctx->lane == 0 ? ctx->scratch_bytes : ctx->scratch2_bytes;
+    if (bytes > arena_bytes) {
+        // free the old block once its lane is idle, then a fresh (larger) one; rounded up to limit regrowth
+        if (arena) {
             KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            KZG_CUDA(ctx, cudaFree(ctx->scratch));
-            ctx->scratch = nullptr;
-            ctx->scratch_bytes = 0;
+            KZG_CUDA(ctx, cudaFree(arena));
+            arena = nullptr;
+            arena_bytes = 0;
         }
         size_t want = bytes + bytes / 8;
-        cudaError_t e = cudaMalloc(&ctx->scratch, want);
+        cudaError_t e = cudaMalloc(&arena, want);
         if (e != cudaSuccess) {
             want = bytes;
-            e = cudaMalloc(&ctx->scratch, want);
+            e = cudaMalloc(&arena, want);
         }
         if (e != cudaSuccess) return set_err(ctx, KZG_ERR_NOMEM, std::string("scratch allocation failed: ") + cudaGetErrorString(e));
-        ctx->scratch_bytes = want;
+        arena_bytes = want;
     }
-    *out = ctx->scratch;
+    *out = arena;
     return KZG_OK;
 }
 
@@ -226,6 +228,12 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
         }
         ctx->own_stream = true;
     }
+    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return KZG_ERR_CUDA;
+    }
     ctx->pinned_bytes = 1 << 16;
     ctx->dev_small_bytes = 1 << 16;
     if (cudaMallocHost((void**)&ctx->pinned, ctx->pinned_bytes) != cudaSuccess ||
@@ -268,6 +276,13 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     for (auto& t : ctx->coset_tables) cudaFree(t.inv_nx);
     cudaFree(ctx->scratch);
+    cudaFree(ctx->scratch2);
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaFree(ctx->dev_small);
     cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -781,6 +781,47 @@ int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t c
     return KZG_OK;
 }
 
+// Independent MSMs (the commitments of one prover round): MSM i is issued on lane i & 1 -- lane 1 is the
+// context's auxiliary stream with its own scratch arena -- so that the latency-bound tail of one (bucket
+// reduction, inversion) overlaps the pipe-bound bucket accumulation of the other.  Every job leaves its affine
+// result in its own 64-byte slot; one D2H copy and one synchronisation fetch them all.
+int msm_run_batch(kzg_ctx* ctx, const MsmJob* jobs, uint32_t count, uint8_t* out_affine) {
+    if (count == 0) return KZG_OK;
+    if (count > 30) return set_err(ctx, KZG_ERR_ARG, "at most 30 commitments per batch");
+    G1Affine* affine_slots = (G1Affine*)(ctx->dev_small + 4096);    // 30 x 64 B
+    G1XYZZ* xyzz_slots = (G1XYZZ*)(ctx->dev_small + 8192);          // 30 x 128 B
+    cudaStream_t main_stream = ctx->stream;
+    int r = KZG_OK;
+    const bool two_lanes = count > 1;
+    if (two_lanes) {
+        // lane 1 may start once everything queued so far on the main stream (the scalars' producers) is done
+        KZG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+        KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    }
+    for (uint32_t i = 0; i < count && r == KZG_OK; i++) {
+        const int lane = two_lanes ? (int)(i & 1) : 0;
+        ctx->lane = lane;
+        ctx->stream = lane ? ctx->aux_stream : main_stream;
+        r = msm_run(ctx, jobs[i].bases, jobs[i].src, jobs[i].n, xyzz_slots + i);
+        if (r == KZG_OK) {
+            KZG_LAUNCH(ctx, g1_finish_kernel, 1, 32, 0, xyzz_slots + i, 1u, affine_slots + i);
+            if (cudaGetLastError() != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, "g1_finish launch failed");
+        }
+    }
+    ctx->lane = 0;
+    ctx->stream = main_stream;
+    if (two_lanes) {
+        // join: the main stream continues only after lane 1 has drained (also on the error path)
+        cudaEventRecord(ctx->ev_join, ctx->aux_stream);
+        cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
+    }
+    KZG_TRY(r);
+    KZG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 1024, affine_slots, 64 * count, cudaMemcpyDeviceToHost, main_stream));
+    KZG_CUDA(ctx, cudaStreamSynchronize(main_stream));
+    memcpy(out_affine, ctx->pinned + 1024, 64 * count);
+    return KZG_OK;
+}
+
 // build (or rebuild) the window table of an SRS; c = 0 picks the window from the SRS size
 int srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t c) {
     if (srs->table) {

@@ -143,6 +143,18 @@ static int dev_alloc(kzg_prover* p, uint64_t count, Fr** out) {
     return KZG_OK;
 }
 
+// the commitments of one round: independent MSMs, issued together (two lanes), fetched with one copy
+static int commit_many(kzg_prover* p, const Fr* const* coefs, const uint64_t* lens, uint32_t count, uint8_t* out) {
+    kzg_ctx* ctx = p->ctx;
+    std::vector<MsmJob> jobs(count);
+    for (uint32_t i = 0; i < count; i++) {
+        jobs[i].bases = srs_bases(ctx, p->srs, 0);
+        jobs[i].src = MsmScalarSrc{coefs[i], true};
+        jobs[i].n = lens[i] < p->srs->n ? lens[i] : p->srs->n;
+    }
+    return msm_run_batch(ctx, jobs.data(), count, out);
+}
+
 static int commit_dev(kzg_prover* p, const Fr* coef, uint64_t len, uint8_t out[64]) {
     kzg_ctx* ctx = p->ctx;
     uint64_t npts = len < p->srs->n ? len : p->srs->n;
@@ -280,24 +292,24 @@ int kzg_prover_round1(kzg_prover* p, const uint8_t* const* evals_f_std, const ui
         KZG_CUDA(ctx, cudaMemcpyAsync(p->ev_self, sel_f, bytes, cudaMemcpyHostToDevice, ctx->stream));
         KZG_CUDA(ctx, cudaMemcpyAsync(p->ev_selt, sel_t, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    uint8_t* out = commitments_out;
+    std::vector<const Fr*> coefs;
     for (uint32_t i = 0; i < p->k; i++) {
         KZG_TRY(fr_convert(ctx, p->ev_f[i], p->ev_f[i], n, true));  // Fr.batchToMontgomery (:147)
         KZG_TRY(fr_convert(ctx, p->ev_t[i], p->ev_t[i], n, true));  // (:148)
         KZG_TRY(ntt_run(ctx, p->ev_f[i], n, p->co_f[i], p->n_bits, true));  // Polynomial.fromEvaluations (:151)
         KZG_TRY(ntt_run(ctx, p->ev_t[i], n, p->co_t[i], p->n_bits, true));  // (:152)
-        KZG_TRY(commit_dev(p, p->co_f[i], n, out));  // (:161)
-        out += 64;
-        KZG_TRY(commit_dev(p, p->co_t[i], n, out));  // (:162)
-        out += 64;
+        coefs.push_back(p->co_f[i]);  // commit (:161)
+        coefs.push_back(p->co_t[i]);  // commit (:162)
     }
     if (p->selected) {
         KZG_TRY(ntt_run(ctx, p->ev_self, n, p->co_self, p->n_bits, true));  // (:170-171)
         KZG_TRY(ntt_run(ctx, p->ev_selt, n, p->co_selt, p->n_bits, true));
-        KZG_TRY(commit_dev(p, p->co_self, n, out));  // (:173)
-        out += 64;
-        KZG_TRY(commit_dev(p, p->co_selt, n, out));  // (:174)
+        coefs.push_back(p->co_self);  // commit (:173)
+        coefs.push_back(p->co_selt);  // commit (:174)
     }
+    // all the round's commitments are independent: issue them together, in the reference's output order
+    std::vector<uint64_t> lens(coefs.size(), n);
+    KZG_TRY(commit_many(p, coefs.data(), lens.data(), (uint32_t)coefs.size(), commitments_out));
     p->round = 1;
     return KZG_OK;
 }
@@ -552,7 +564,6 @@ int kzg_prover_round5(kzg_prover* p, const uint8_t v_bytes[32], uint8_t out_w[12
     int r = poly_linear_combination(ctx, wnum, wlen, polys.data(), lens.data(), coeffs.data(), (uint32_t)polys.size(), constant);
     if (r == KZG_OK) r = poly_div_x_sub(ctx, wnum, wlen, xi, wq, &exact1);
     if (r == KZG_OK && !exact1) r = set_err(ctx, KZG_ERR_PROTOCOL, "Polynomial does not divide");
-    if (r == KZG_OK) r = commit_dev(p, wq, wlen, out_w);
     // W_xiw = (acc(X) - acc(xi w)) / (X - xi w)
     if (r == KZG_OK) {
         const Fr* ps[1] = {p->co_acc};
@@ -563,7 +574,11 @@ int kzg_prover_round5(kzg_prover* p, const uint8_t v_bytes[32], uint8_t out_w[12
     const Fr xiw = h_mul(xi, fr_root_of_unity(p->n_bits));
     if (r == KZG_OK) r = poly_div_x_sub(ctx, wnum, n, xiw, wq2, &exact2);
     if (r == KZG_OK && !exact2) r = set_err(ctx, KZG_ERR_PROTOCOL, "Polynomial does not divide");
-    if (r == KZG_OK) r = commit_dev(p, wq2, n, out_w + 64);
+    if (r == KZG_OK) {  // [W_xi], [W_xiw] (:409-410): two independent commitments
+        const Fr* coefs[2] = {wq, wq2};
+        uint64_t lens[2] = {wlen, n};
+        r = commit_many(p, coefs, lens, 2, out_w);
+    }
     cudaFreeAsync(tmp, ctx->stream);
     KZG_TRY(r);
     p->round = 5;
