@@ -301,7 +301,10 @@ def run_b200(args):
     peaks, peak_kind = measured_peaks()
     roofline = {
         "bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": imad.value / 1e12,
-        "unit": "Tmac/s", "frac": achieved / (imad.value / 1e12) if imad.value else None, "traffic": None,
+        "unit": "Tmac/s", "frac": achieved / (imad.value / 1e12) if imad.value else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 points on one GPU, from the ncu --set full
+        # capture summarised in profiles/r01_msm_accumulate_full.md (64-byte random gathers cost 128 B each)
+        "traffic": 2.944e10 if (world == 1 and args.log_n == 24) else None,
         "peak_source": "kzg_bench_imad_peak: IMAD.WIDE.U32 carry chains timed live on this GPU (MEASURED_PEAKS.json has no integer peak)",
         "modmul_peak_tmacs": modmul.value / 1e12,
         "algorithmic_macs_per_launch": macs_per_launch, "executed_macs_per_launch": executed_macs,
@@ -311,6 +314,11 @@ def run_b200(args):
         "windows": geom["windows"], "window_bits": geom["c"],
         "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_kind": peak_kind,
     }
+
+    # ---- the HBM-side kernels: one NTT of the size the n = 2^22 prover needs (2^24), timed live (rank 0) ----
+    roofline_hbm = None
+    if rank == 0 and world == 1:
+        roofline_hbm = bench_ntt(curve, 24, peaks.get("hbm_gbs"), peak_kind)
 
     # ---- grand-sum prove at n = 2^prove_log_n through the drop-in entry point (rank 0 only) ----
     prove = None
@@ -356,7 +364,7 @@ def run_b200(args):
             "e2e": {"value": N / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * shard, "d2h_bytes_per_step": 64},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "prove": prove,
+            "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "prove": prove,
         }
         print(json.dumps(line))
     if world > 1:
@@ -389,6 +397,34 @@ def known_answer_matches(curve, k, got_affine):
     aff = bytearray(64)
     curve.check(curve.lib.kzg_g1_msm_affine(curve.ctx, as_ptr(gen), as_ptr(k.to_bytes(32, "little")), 1, 0, as_ptr(aff), None))
     return bytes(aff) == bytes(got_affine)
+
+
+def bench_ntt(curve, log_n, hbm_peak, peak_kind):
+    """Fr NTT of 2^log_n elements, CUDA events on the launching stream; algorithmic bytes = 64 N"""
+    import torch
+    from kzg_grandsums_study_b200 import synthetic
+    n = 1 << log_n
+    x = curve.to_device(synthetic.random_fr_std(77, n).tobytes())
+    y = curve.alloc(n)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    best = None
+    for i in range(6):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        curve.check(curve.lib.kzg_fr_ntt(curve.ctx, x.handle, y.handle, 0))
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            t = a.elapsed_time(b)
+            best = t if best is None else min(best, t)
+    achieved = 64.0 * n / (best * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "ntt_strided_pass_kernel x2 + ntt_last_pass_kernel (one 2^%d transform)" % log_n,
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if hbm_peak else None,
+            "peak_kind": peak_kind, "ms": best,
+            # dram bytes of the three passes from profiles/r01_ntt24_full.md (one read + one write of the vector per pass)
+            "traffic": 3.07e9 if log_n == 24 else None,
+            "note": "3 shared-memory passes; each is bound by the integer pipe (fmaheavy 74-81 % in ncu), not by HBM"}
 
 
 def bench_prove(curve, log_n, steps, tau):

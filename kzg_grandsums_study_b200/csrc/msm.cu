@@ -964,19 +964,36 @@ int kzg_g1_partials_combine(kzg_ctx* ctx, const void* partials_dev, uint32_t cou
     return msm_result_to_host_affine(ctx, (const G1XYZZ*)partials_dev, count, out_affine);
 }
 
-// scalars from host memory against a resident SRS (the e2e path of bench.py: H2D of the scalars is inside)
+// scalars from host memory against a resident SRS (the e2e path of bench.py: H2D of the scalars is inside).
+// Large inputs are split in two halves: the second half's upload runs on the auxiliary stream (copy engine) while
+// the first half's MSM computes; the two partial points are added by g1_finish.  (The overlap needs pinned host
+// memory; with pageable memory the call is still correct, just serial.)
 int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
                      uint8_t out_affine[64]) {
     if (!ctx || !srs || (!scalars_std_host && n) || !out_affine) return KZG_ERR_ARG;
     if (first + n > srs->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
     Fr* tmp = nullptr;
-    if (n) {
-        KZG_CUDA(ctx, cudaMallocAsync((void**)&tmp, sizeof(Fr) * n, ctx->stream));
-        KZG_CUDA(ctx, cudaMemcpyAsync(tmp, scalars_std_host, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) KZG_CUDA(ctx, cudaMallocAsync((void**)&tmp, sizeof(Fr) * n, ctx->stream));
+    const Fr* host = (const Fr*)scalars_std_host;
+    G1XYZZ* slots = (G1XYZZ*)(ctx->dev_small + 8192);
+    int r = KZG_OK;
+    uint32_t parts = 1;
+    if (n >= (1ull << 22)) {
+        const uint64_t h = n / 2;
+        parts = 2;
+        KZG_CUDA(ctx, cudaMemcpyAsync(tmp, host, sizeof(Fr) * h, cudaMemcpyHostToDevice, ctx->stream));
+        KZG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));          // tmp exists from here on
+        KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+        KZG_CUDA(ctx, cudaMemcpyAsync(tmp + h, host + h, sizeof(Fr) * (n - h), cudaMemcpyHostToDevice, ctx->aux_stream));
+        KZG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+        r = msm_run(ctx, srs_bases(ctx, srs, first), MsmScalarSrc{tmp, false}, h, slots);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);  // (also on the error path: tmp is freed on this stream)
+        if (r == KZG_OK) r = msm_run(ctx, srs_bases(ctx, srs, first + h), MsmScalarSrc{tmp + h, false}, n - h, slots + 1);
+    } else {
+        if (n) KZG_CUDA(ctx, cudaMemcpyAsync(tmp, host, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+        r = msm_run(ctx, srs_bases(ctx, srs, first), MsmScalarSrc{tmp, false}, n, slots);
     }
-    MsmScalarSrc src{tmp, false};
-    int r = msm_run(ctx, srs_bases(ctx, srs, first), src, n, result_slot(ctx));
-    if (r == KZG_OK) r = msm_result_to_host_affine(ctx, result_slot(ctx), 1, out_affine);
+    if (r == KZG_OK) r = msm_result_to_host_affine(ctx, slots, parts, out_affine);
     if (tmp) cudaFreeAsync(tmp, ctx->stream);
     return r;
 }

@@ -9,9 +9,21 @@ LIB = os.path.join(HERE, "libkzgoracle.so")
 FLAGS = ["-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-std=gnu11", "-Wall"]
 
 
+def _cpu_id():
+    """-march=native ties the binary to the build host: rebuild when the library travels to a different CPU"""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return hashlib.sha256(line.encode()).hexdigest()[:16]
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(verbose=False):
     with open(SRC, "rb") as f:
-        digest = hashlib.sha256(f.read() + " ".join(FLAGS).encode()).hexdigest()
+        digest = hashlib.sha256(f.read() + " ".join(FLAGS).encode() + _cpu_id().encode()).hexdigest()
     stamp = LIB + ".stamp"
     if os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         if verbose:
