@@ -216,3 +216,39 @@ def test_column_buffer_types(curve, tau, ptau_factory):
         ea, eb = Evaluations(a, curve), Evaluations(b, curve)
         assert ea.length() == 1 << nbits and ea.getEvaluation(3) == fb[96:128]
         assert pr.proof_bytes(mset_eq_kzg_grandsum_prover(path, ea, eb)) == ref
+
+
+@pytest.mark.parametrize("nbits", [20, 22])
+def test_config_c4_full_size_properties(nbits, curve, tau, ptau_factory):
+    """BASELINE C4 (n = 2^20, 2^22; T = PRNG permutation of F): sizes the Python oracle cannot reach.  Size-independent
+    properties: the proof is accepted by the drop-in verifier (real pairing against [tau]_2 of the same .ptau) and by
+    the oracle's trapdoor check; [F] and [T] equal the closed forms F(tau) G1 / T(tau) G1 computed through a different
+    device path (Horner evaluation + fixed-base product); a tampered proof is rejected; the proof is reproducible."""
+    import numpy as np
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200.grandsum import mset_eq_kzg_grandsum_prover, mset_eq_kzg_grandsum_verifier
+    from kzg_grandsums_study_b200.polynomial import Evaluations, Polynomial
+    n = 1 << nbits
+    f = synthetic.random_fr_std(4 if nbits == 20 else 5, n)
+    t = np.ascontiguousarray(f[synthetic.permutation(4 if nbits == 20 else 5, n)])
+    path = ptau_factory(nbits)
+    proof = mset_eq_kzg_grandsum_prover(path, Evaluations(f, curve), Evaluations(t, curve))
+    assert list(proof["commitments"]) == ["F", "T", "S", "Q", "Wxi", "Wxiw"]
+    assert mset_eq_kzg_grandsum_verifier(path, proof, nbits) is True
+    assert pr.grandsum_verifier(proof, nbits, tau=tau)
+    # closed forms: commit(p) = p(tau) G1 with p = iNTT(batchToMontgomery(column))
+    for name, col in (("F", f), ("T", t)):
+        p = Polynomial.fromEvaluations(curve.Fr.batchToMontgomery(col.tobytes()), curve)
+        p_tau = bn.fr_from_mont_bytes(p.evaluate(bn.fr_to_mont_bytes(tau)))
+        assert proof["commitments"][name] == bn.g1_to_bytes(bn.g1_mul_gen(p_tau)), name
+    again = mset_eq_kzg_grandsum_prover(path, Evaluations(f, curve), Evaluations(t, curve))
+    assert pr.proof_bytes(again) == pr.proof_bytes(proof)
+    bad = {"commitments": dict(proof["commitments"]), "evaluations": dict(proof["evaluations"])}
+    bad["evaluations"]["sxiw"] = bn.fr_to_mont_bytes(7)
+    assert mset_eq_kzg_grandsum_verifier(path, bad, nbits) is False
+    # multisets that differ in one element are refused with the reference's message
+    t2 = t.copy()
+    t2[12345, 0] ^= np.uint64(1)
+    from kzg_grandsums_study_b200 import KzgError
+    with pytest.raises(KzgError, match="The grand-sum polynomial S is not well calculated"):
+        mset_eq_kzg_grandsum_prover(path, Evaluations(f, curve), Evaluations(t2, curve))
