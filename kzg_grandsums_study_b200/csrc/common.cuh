@@ -37,6 +37,7 @@ struct kzg_ctx {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int lane = 0;
+    bool no_split = false;  // KZGB200_NO_SPLIT=1: mid-sized MSMs are not split over the two lanes (A/B timing)
     // persistent scratch per lane (grown on demand)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -120,6 +121,7 @@ struct MsmBases {
     uint32_t tab_c, tab_nwin;
 };
 int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev);
+int msm_run_split(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev);
 MsmBases srs_bases(kzg_ctx* ctx, const kzg_srs* srs, uint64_t first);
 int srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t c);
 int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t count, uint8_t out[64]);

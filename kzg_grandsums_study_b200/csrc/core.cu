@@ -1,4 +1,5 @@
 // Context, device buffers and the bulk-Fr / Polynomial C ABI of libkzgb200.so.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -234,6 +235,7 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
         delete ctx;
         return KZG_ERR_CUDA;
     }
+    ctx->no_split = getenv("KZGB200_NO_SPLIT") != nullptr;
     ctx->pinned_bytes = 1 << 16;
     ctx->dev_small_bytes = 1 << 16;
     if (cudaMallocHost((void**)&ctx->pinned, ctx->pinned_bytes) != cudaSuccess ||

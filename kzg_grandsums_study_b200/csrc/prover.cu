@@ -160,7 +160,7 @@ static int commit_dev(kzg_prover* p, const Fr* coef, uint64_t len, uint8_t out[6
     uint64_t npts = len < p->srs->n ? len : p->srs->n;
     G1XYZZ* slot = (G1XYZZ*)(ctx->dev_small + 1024);
     MsmScalarSrc src{coef, true};
-    KZG_TRY(msm_run(ctx, srs_bases(ctx, p->srs, 0), src, npts, slot));
+    KZG_TRY(msm_run_split(ctx, srs_bases(ctx, p->srs, 0), src, npts, slot));
     return msm_result_to_host_affine(ctx, slot, 1, out);
 }
 
