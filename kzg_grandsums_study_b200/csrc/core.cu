@@ -167,6 +167,11 @@ __global__ void selftest_kernel(uint32_t n, unsigned int* fail) {
     if ((i & 63) == 0) {
         Fq a = random_fp<FqP>(s);
         if (!fp_is_zero(a)) ok &= fp_eq(fp_mul(a, fp_inv(a)), fp_one<FqP>());
+        ok &= fp_eq(fp_inv(a), fp_inv_fermat(a));  // binary extended Euclid == a^(p-2)
+        Fr b = random_fp<FrP>(s);
+        ok &= fp_eq(fp_inv(b), fp_inv_fermat(b));
+        ok &= fp_is_zero(fp_inv(fp_zero<FrP>())) && fp_eq(fp_inv(fp_one<FqP>()), fp_one<FqP>());
+        ok &= fp_eq(fp_inv(fp_neg(fp_one<FqP>())), fp_neg(fp_one<FqP>()));
         // group law on the generator (1, 2): 2G + G == G + G + G, (G + G) via madd hits the doubling branch
         G1Affine g;
         g.x = fp_one<FqP>();
