@@ -295,7 +295,8 @@ class Curve(HostCurve):
             power = C.c_uint32()
             self.check(self.lib.kzg_srs_load_ptau(self.ctx, ptau_path.encode(), n_points, C.byref(h), C.byref(power)))
             if os.environ.get("KZGB200_NO_SRS_TABLE") != "1":
-                self.check(self.lib.kzg_srs_precompute(self.ctx, h, 0))   # one-off window table (msm.cu)
+                c = int(os.environ.get("KZGB200_TABLE_WINDOW", "0"))        # 0 = the library's cost model
+                self.check(self.lib.kzg_srs_precompute(self.ctx, h, c))   # one-off window table (msm.cu)
             self._srs_cache[key] = (h, power.value)
         return self._srs_cache[key]
 
