@@ -107,6 +107,8 @@ class Polynomial:
 
     def evaluate(self, x):                            # polynomial.js:228-238 (Horner)
         res = 0
+        if not self.coef:                             # empty buffer (divZh of the zero polynomial): the zero polynomial
+            return 0
         for i in range(self.degree(), -1, -1):
             res = (self.coef[i] + res * x) % R
         return res

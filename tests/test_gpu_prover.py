@@ -252,3 +252,87 @@ def test_config_c4_full_size_properties(nbits, curve, tau, ptau_factory):
     from kzg_grandsums_study_b200 import KzgError
     with pytest.raises(KzgError, match="The grand-sum polynomial S is not well calculated"):
         mset_eq_kzg_grandsum_prover(path, Evaluations(f, curve), Evaluations(t2, curve))
+
+
+def _prove_pair(kind, curve, tau, ptau_factory, nbits, cols_f, cols_t, sel_f=None, sel_t=None):
+    """GPU proof and oracle proof for explicit integer columns (selectors: lists of 0/1 or None)"""
+    from kzg_grandsums_study_b200.grandsum import mset_eq_kzg_grandsum_prover
+    from kzg_grandsums_study_b200.grandproduct import mset_eq_kzg_grandproduct_prover
+    from kzg_grandsums_study_b200.polynomial import Evaluations
+    path = ptau_factory(nbits)
+    fb = [bn.fr_vec_to_std_bytes(c) for c in cols_f]
+    tb = [bn.fr_vec_to_std_bytes(c) for c in cols_t]
+    sfb = bn.fr_vec_to_mont_bytes(sel_f) if sel_f is not None else None
+    stb = bn.fr_vec_to_mont_bytes(sel_t) if sel_t is not None else None
+    ev = lambda b: Evaluations(b, curve)
+    gpu = mset_eq_kzg_grandsum_prover if kind == "gs" else mset_eq_kzg_grandproduct_prover
+    cpu = pr.grandsum_prover if kind == "gs" else pr.grandproduct_prover
+    got = gpu(path, [ev(b) for b in fb], [ev(b) for b in tb], ev(sfb) if sfb else None, ev(stb) if stb else None)
+    want = cpu(pr.TrapdoorSrs(tau, nbits), fb, tb, sfb, stb)
+    run_both.last_path = path
+    return got, want
+
+
+@pytest.mark.parametrize("kind", ["gs", "gp"])
+def test_randomised_shapes(kind, curve, tau, ptau_factory):
+    """a seeded sweep over (nBits, k, selectors, selector density): GPU proof == oracle proof, byte for byte"""
+    import random
+    rng = random.Random(20261018 if kind == "gs" else 7)
+    for case in range(24):
+        nbits = rng.randint(1, 9)
+        n = 1 << nbits
+        k = rng.choice([1, 1, 2, 3, 5])
+        selected = rng.random() < 0.5 and n >= 4
+        cols_f = [inputs.random_column(rng.randrange(1 << 30), n) for _ in range(k)]
+        if selected:
+            # binary selectors with the same number of ones on both sides; selected rows of T are a permutation of the
+            # selected rows of F (row-wise across the k columns), unselected rows are unrelated
+            ones = rng.randint(1, n - 1)
+            rows_f = sorted(rng.sample(range(n), ones))
+            rows_t = sorted(rng.sample(range(n), ones))
+            perm = rows_f[:]
+            rng.shuffle(perm)
+            cols_t = [inputs.random_column(rng.randrange(1 << 30), n) for _ in range(k)]
+            for dst, src in zip(rows_t, perm):
+                for c in range(k):
+                    cols_t[c][dst] = cols_f[c][src]
+            sel_f = [1 if i in set(rows_f) else 0 for i in range(n)]
+            sel_t = [1 if i in set(rows_t) else 0 for i in range(n)]
+        else:
+            perm = list(range(n))
+            rng.shuffle(perm)
+            cols_t = [[c[perm[i]] for i in range(n)] for c in cols_f]
+            sel_f = sel_t = None
+        got, want = _prove_pair(kind, curve, tau, ptau_factory, nbits, cols_f, cols_t, sel_f, sel_t)
+        assert pr.proof_bytes(got) == pr.proof_bytes(want), (case, nbits, k, selected)
+        assert list(got["commitments"]) == list(want["commitments"])
+    assert package_verify(kind, got, nbits) is True
+
+
+@pytest.mark.parametrize("kind", ["gs", "gp"])
+def test_degenerate_columns(kind, curve, tau, ptau_factory):
+    """inputs outside the reference's comfort zone where the mathematically correct result is still
+    well defined: all-zero columns (every commitment is the point at infinity), constant columns (degree-0 witness
+    polynomials), repeated values, small values"""
+    n = 16
+    for cols in ([0] * n, [7] * n, [1, 2] * (n // 2), list(range(n)), [R - 1] * n, [0] * (n - 1) + [5]):
+        f = list(cols)
+        t = f[3:] + f[:3]
+        got, want = _prove_pair(kind, curve, tau, ptau_factory, 4, [f], [t])
+        assert pr.proof_bytes(got) == pr.proof_bytes(want), cols[:4]
+    zero = _prove_pair(kind, curve, tau, ptau_factory, 4, [[0] * n], [[0] * n])[0]
+    assert zero["commitments"]["F"] == bytes(64) and zero["commitments"]["T"] == bytes(64)
+
+
+def test_column_count_limits(curve, tau, ptau_factory):
+    """k = 11 columns work; more are refused with a clear message (the fused linear combinations take 28 terms)"""
+    from kzg_grandsums_study_b200 import KzgError
+    n = 8
+    cols_f = [inputs.random_column(500 + i, n) for i in range(11)]
+    cols_t = [inputs.rotate_right(c) for c in cols_f]
+    got, want = _prove_pair("gs", curve, tau, ptau_factory, 3, cols_f, cols_t)
+    assert pr.proof_bytes(got) == pr.proof_bytes(want)
+    cols_f.append(inputs.random_column(999, n))
+    cols_t.append(inputs.rotate_right(cols_f[-1]))
+    with pytest.raises(KzgError, match="at most 11 columns"):
+        _prove_pair("gs", curve, tau, ptau_factory, 3, cols_f, cols_t)
