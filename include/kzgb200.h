@@ -179,6 +179,10 @@ int kzg_prover_round3(kzg_prover* p, const uint8_t alpha[32], uint8_t out_q[64])
 int kzg_prover_round4(kzg_prover* p, const uint8_t xi[32], uint8_t* evals_out);
 /* round 5 (:320-413): out: [Wxi] || [Wxiw] */
 int kzg_prover_round5(kzg_prover* p, const uint8_t v[32], uint8_t out_w[128]);
+/* After round 5: hand the Montgomery-form evaluations of column `column` (which = 0: F, 1: T) to the caller as a
+ * device vector (ownership moves; free with kzg_buf_free).  The reference REPLACES evalsFs[i].eval / evalsTs[i].eval
+ * by their Montgomery form as a side effect of proving (prover.js:147-148); the host layer reproduces that with this. */
+int kzg_prover_take_evals(kzg_prover* p, uint32_t column, int which, kzg_buf** out);
 /* number of evaluations / commitments round 4 / round 1 write */
 uint32_t kzg_prover_n_evals(kzg_prover* p);
 uint32_t kzg_prover_n_round1_commitments(kzg_prover* p);

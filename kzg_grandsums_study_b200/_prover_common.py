@@ -147,6 +147,12 @@ def prove(kind, pTauFilename, evalsFs, evalsTs, evalsSelF=None, evalsSelT=None, 
         curve.check(lib.kzg_prover_round5(prover, as_ptr(v), as_ptr(out5)))
         Cm["Wxi"] = bytes(out5[:64])
         Cm["Wxiw"] = bytes(out5[64:])
+        # side effect of the reference (:147-148): the callers' F / T evaluations are now in Montgomery form
+        for i in range(nPols):
+            for which, ev in ((0, evalsFs[i]), (1, evalsTs[i])):
+                h = C.c_void_p()
+                curve.check(lib.kzg_prover_take_evals(prover, i, which, C.byref(h)))
+                ev.eval = curve.wrap(h)
         if trace is not None:
             trace["challenges"] = challenges
         return proof

@@ -120,8 +120,9 @@ __device__ __forceinline__ Fr shfl_fr(const Fr& v, uint32_t src) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// batch inverse: Montgomery trick per thread (E elements), prefix and suffix products across the
-// warp by shuffles, ONE Fermat inversion per warp (32 * E elements).  Zero maps to zero.
+// batch inverse, base case (<= 4096 elements): Montgomery trick per thread (E elements), prefix and suffix
+// products across the warp by shuffles, ONE inversion per warp (32 * E elements).  Zero maps to zero.
+// Larger inputs go through the two-level scheme below (fr_batch_inverse).
 // ------------------------------------------------------------------------------------------------
 constexpr int BI_E = 8;
 __global__ void __launch_bounds__(EW_THREADS) batch_inverse_kernel(const Fr* __restrict__ in, Fr* __restrict__ out,

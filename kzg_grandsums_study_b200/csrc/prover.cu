@@ -178,6 +178,25 @@ uint32_t kzg_prover_n_evals(kzg_prover* p) {
 }
 uint32_t kzg_prover_n_round1_commitments(kzg_prover* p) { return p ? 2 * p->k + (p->selected ? 2 : 0) : 0; }
 
+int kzg_prover_take_evals(kzg_prover* p, uint32_t column, int which, kzg_buf** out) {
+    if (!p || !out || column >= p->k || (which != 0 && which != 1)) return KZG_ERR_ARG;
+    kzg_ctx* ctx = p->ctx;
+    if (p->round < 5) return set_err(ctx, KZG_ERR_ARG, "evaluations can be taken after round 5 only");
+    Fr*& slot = which == 0 ? p->ev_f[column] : p->ev_t[column];
+    if (!slot) return set_err(ctx, KZG_ERR_ARG, "evaluations already taken");
+    for (size_t i = 0; i < p->owned.size(); i++)
+        if (p->owned[i] == (void*)slot) {
+            p->owned.erase(p->owned.begin() + i);
+            break;
+        }
+    kzg_buf* b = new kzg_buf();
+    b->d = slot;
+    b->n = p->n;
+    slot = nullptr;
+    *out = b;
+    return KZG_OK;
+}
+
 int kzg_prover_destroy(kzg_prover* p) {
     if (!p) return KZG_OK;
     for (void* d : p->owned) cudaFreeAsync(d, p->ctx->stream);

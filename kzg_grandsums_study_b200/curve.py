@@ -244,6 +244,7 @@ class Curve(HostCurve):
             raise KzgError(rc, msg.decode() if msg else "kzg error %d" % rc)
 
     def alloc(self, n, zero=True):
+        """a zero-filled device vector of n elements (kzg_buf_alloc always clears, like `new Uint8Array`)"""
         h = C.c_void_p()
         self.check(self.lib.kzg_buf_alloc(self.ctx, n, C.byref(h)))
         return DeviceBuffer(self, h)

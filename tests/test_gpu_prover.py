@@ -336,3 +336,18 @@ def test_column_count_limits(curve, tau, ptau_factory):
     cols_t.append(inputs.rotate_right(cols_f[-1]))
     with pytest.raises(KzgError, match="at most 11 columns"):
         _prove_pair("gs", curve, tau, ptau_factory, 3, cols_f, cols_t)
+
+
+def test_prover_replaces_evals_by_montgomery_form(curve, tau, ptau_factory):
+    """prover.js:147-148: evalsFs[i].eval / evalsTs[i].eval are replaced by their Montgomery form"""
+    from kzg_grandsums_study_b200.grandsum import mset_eq_kzg_grandsum_prover
+    from kzg_grandsums_study_b200.polynomial import Evaluations
+    n = 32
+    cols = [inputs.random_column(70 + i, n) for i in range(2)]
+    evf = [Evaluations(bn.fr_vec_to_std_bytes(c), curve) for c in cols]
+    evt = [Evaluations(bn.fr_vec_to_std_bytes(inputs.rotate_right(c)), curve) for c in cols]
+    mset_eq_kzg_grandsum_prover(ptau_factory(5), evf, evt)
+    for c, ef, et in zip(cols, evf, evt):
+        assert ef.tobytes() == bn.fr_vec_to_mont_bytes(c)
+        assert et.tobytes() == bn.fr_vec_to_mont_bytes(inputs.rotate_right(c))
+        assert ef.length() == n and ef.getEvaluation(3) == bn.fr_to_mont_bytes(c[3])

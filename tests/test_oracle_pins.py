@@ -185,3 +185,15 @@ def test_oracle_reproduces_golden_fixtures():
         proof = prover(pr.TrapdoorSrs(tau, g["ptau_power"]), [bn.fr_vec_to_std_bytes(c) for c in cf],
                        [bn.fr_vec_to_std_bytes(c) for c in ct], sf, st)
         assert pr.proof_bytes(proof).hex() == g["proof_bytes"], name
+
+
+def test_reference_polynomial_kats():
+    """the small-integer known answers of the reference's test/polynomial.test.js for methods on the prover path:
+    evaluate (:116-124) and multiply (:207-220)"""
+    P = poly.Polynomial
+    assert P([0, 1, 2, 3]).evaluate(2) == 34
+    prod = P([2, 0, bn.R - 3, 2]).multiply(P([0, 3, 1]))
+    assert prod.coef[:6] == [0, 6, 2, bn.R - 9, 3, 2] and not any(prod.coef[6:])
+    # divByXSubValue inverts byXSubValue's KAT (:255-262): (7x^2 - 3x + 4)(x - 6) = 7x^3 - 45x^2 + 22x - 24
+    q = P([bn.R - 24, 22, bn.R - 45, 7]).div_by_x_sub_value(6)
+    assert q.coef == [4, bn.R - 3, 7, 0]
