@@ -19,7 +19,7 @@ struct kzg_ctx {
     uint32_t msm_window = 0;  // 0 = auto
     // optional per-kernel device timing (bench.py's live roofline): event pairs around tagged launches
     bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[2];
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[5];
     std::vector<cudaEvent_t> event_pool;
     // twiddle tables (device): W = w_{2^26}; lo[i] = W^i, hi[j] = W^(j * 8192); [0] forward, [1] inverse
     kzg::Fr* tw_lo[2] = {nullptr, nullptr};
@@ -98,7 +98,8 @@ int set_err(kzg_ctx* ctx, int code, const std::string& msg);
 #define KZG_CHECK_LAUNCH(ctx) KZG_CUDA(ctx, cudaGetLastError())
 
 // tags for kzg_ctx_kernel_time
-enum { KZG_TIMED_MSM_ACCUMULATE = 0, KZG_TIMED_NTT = 1 };
+enum { KZG_TIMED_MSM_ACCUMULATE = 0, KZG_TIMED_NTT = 1, KZG_TIMED_MSM_SORT = 2, KZG_TIMED_MSM_REDUCE = 3,
+       KZG_TIMED_MSM_FINISH = 4, KZG_TIMED_TAGS = 5 };
 void timed_begin(kzg_ctx* ctx, int tag);
 void timed_end(kzg_ctx* ctx, int tag);
 

@@ -275,7 +275,7 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
         cudaFree(ctx->tw_lo[d]);
         cudaFree(ctx->tw_hi[d]);
     }
-    for (int tag = 0; tag < 2; tag++)
+    for (int tag = 0; tag < KZG_TIMED_TAGS; tag++)
         for (auto& pr : ctx->timed[tag]) {
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
@@ -365,7 +365,7 @@ int kzg_bench_modmul_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second) {
 }
 
 int kzg_ctx_kernel_time(kzg_ctx* ctx, uint32_t which, int reset, double* ms_out, uint64_t* launches_out) {
-    if (!ctx || which > 1) return KZG_ERR_ARG;
+    if (!ctx || which >= KZG_TIMED_TAGS) return KZG_ERR_ARG;
     KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double total = 0;
     for (auto& pr : ctx->timed[which]) {
@@ -375,7 +375,7 @@ int kzg_ctx_kernel_time(kzg_ctx* ctx, uint32_t which, int reset, double* ms_out,
     if (ms_out) *ms_out = total;
     if (launches_out) *launches_out = ctx->timed[which].size();
     if (reset) {
-        for (int tag = 0; tag < 2; tag++) {
+        for (int tag = 0; tag < KZG_TIMED_TAGS; tag++) {
             for (auto& pr : ctx->timed[tag]) {
                 ctx->event_pool.push_back(pr.first);
                 ctx->event_pool.push_back(pr.second);

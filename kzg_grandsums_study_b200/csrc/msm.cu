@@ -704,6 +704,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nkeys + 1), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), ctx->stream));
     const uint32_t dblocks = (uint32_t)((n + 255) / 256);
+    timed_begin(ctx, KZG_TIMED_MSM_SORT);
     KZG_LAUNCH(ctx, msm_digits_kernel<false>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, counts, nullptr);
     KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums);
     KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, offsets);
@@ -714,11 +715,13 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums, segoff, cursor,
                heavy + 1, heavy);
     KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
+    timed_end(ctx, KZG_TIMED_MSM_SORT);
 
     const uint32_t ablocks = (uint32_t)((max_tasks + 127) / 128);
     timed_begin(ctx, KZG_TIMED_MSM_ACCUMULATE);
     KZG_LAUNCH(ctx, msm_accumulate_kernel, ablocks, 128, 0, pts, sorted, offsets, segoff, nkeys, g.seg, partials);
     timed_end(ctx, KZG_TIMED_MSM_ACCUMULATE);
+    timed_begin(ctx, KZG_TIMED_MSM_REDUCE);
     KZG_LAUNCH(ctx, msm_collapse_kernel, (uint32_t)ctx->sm_count * 2, RED_THREADS, 0, partials, segoff, heavy + 1, heavy);
     {
         const G1XYZZ* in = partials;
@@ -745,6 +748,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         KZG_LAUNCH(ctx, msm_reduce_final_kernel, g.nsets, RED_THREADS, 0, gather_parts, gather_blocks, sums_out);
     }
     if (g.nsets > 1) KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, result_dev);
+    timed_end(ctx, KZG_TIMED_MSM_REDUCE);
 #ifdef KZG_MSM_EXPERIMENT
     if (getenv("KZG_MSM_EXPERIMENT")) {  // timing experiments on the scatter kernel (results are then discarded)
         MsmGeom ge = g;
@@ -773,7 +777,9 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
 int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t count, uint8_t out[64]) {
     static_assert(sizeof(G1Affine) == 64, "affine layout");
     G1Affine* slot = (G1Affine*)ctx->dev_small;
+    timed_begin(ctx, KZG_TIMED_MSM_FINISH);
     KZG_LAUNCH(ctx, g1_finish_kernel, 1, 32, 0, result_dev, count, slot);
+    timed_end(ctx, KZG_TIMED_MSM_FINISH);
     KZG_CHECK_LAUNCH(ctx);
     KZG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, slot, 64, cudaMemcpyDeviceToHost, ctx->stream));
     KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
