@@ -306,11 +306,53 @@ int kzg_ctx_sync(kzg_ctx* ctx) {
 const char* kzg_last_error(kzg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 uint64_t kzg_ctx_launch_count(kzg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// quad-lane group law (ec.cuh) against the scalar formulas: generic sums, doublings through the addition,
+// cancellation, infinities, small multiples.  One case per quad.
+__global__ void selftest_quad_kernel(uint32_t n, unsigned int* fail) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = t >> 2, j = t & 3;
+    if (q >= n) return;
+    const uint32_t qm = quad_mask();
+    G1Affine g;
+    g.x = fp_one<FqP>();
+    g.y = fp_dbl(fp_one<FqP>());
+    const G1XYZZ base = xyzz_from_affine(g);
+    // A = ka G, B = kb G in non-trivial XYZZ representations
+    const uint32_t ka = 2 + (q * 7919u) % 1021u, kb = 2 + (q * 104729u) % 509u;
+    G1XYZZ A = xyzz_mul_small(base, ka), B = xyzz_mul_small(base, kb);
+    const uint32_t kind = q % 8;
+    if (kind == 1) B = A;                                   // doubling through the addition
+    if (kind == 2) { B = A; B.y = fp_neg(B.y); }            // cancellation
+    if (kind == 3) A = xyzz_inf();
+    if (kind == 4) B = xyzz_inf();
+    if (kind == 5) { B = xyzz_mul_small(base, ka); }        // same point, same representation path
+    G1XYZZ want = A;
+    xyzz_add(want, B);
+    Fq a = quad_coord(A, j);
+    quad_add(a, quad_coord(B, j), j, qm);
+    bool ok = fp_eq(a, quad_coord(want, j)) || (xyzz_is_inf(want) && j != 2);  // infinity: only ZZ = 0 is specified
+    if (xyzz_is_inf(want) && j == 2) ok = fp_is_zero(a);
+    G1XYZZ d = xyzz_dbl(A);
+    Fq a2 = quad_coord(A, j);
+    quad_dbl(a2, j, qm);
+    ok &= xyzz_is_inf(d) ? (j != 2 || fp_is_zero(a2)) : fp_eq(a2, quad_coord(d, j));
+    const uint32_t k = q % 300u;
+    G1XYZZ m = xyzz_mul_small(B, k);
+    Fq a3 = quad_coord(B, j);
+    quad_mul_small(a3, k, j, qm);
+    ok &= xyzz_is_inf(m) ? (j != 2 || fp_is_zero(a3)) : fp_eq(a3, quad_coord(m, j));
+    if (!ok) atomicAdd(fail, 1u);
+}
+
 int kzg_selftest(kzg_ctx* ctx, uint32_t n_cases) {
     if (!ctx) return KZG_ERR_ARG;
     unsigned int* slot = (unsigned int*)ctx->dev_small;
     KZG_CUDA(ctx, cudaMemsetAsync(slot, 0, sizeof(unsigned int), ctx->stream));
     KZG_LAUNCH(ctx, selftest_kernel, (n_cases + 127) / 128, 128, 0, n_cases, slot);
+    {
+        const uint32_t quads = n_cases < 2048 ? n_cases : 2048;  // ~300 group operations per case
+        KZG_LAUNCH(ctx, selftest_quad_kernel, (quads * 4 + 127) / 128, 128, 0, quads, slot);
+    }
     KZG_CHECK_LAUNCH(ctx);
     KZG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, slot, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

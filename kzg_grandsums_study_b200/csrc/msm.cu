@@ -20,11 +20,10 @@
 //                         gathers, next point prefetched during the add.
 //                         THE IMAD-bound kernel: 10 modmul (1360 limb MACs) per entry.
 //   5. msm_collapse       buckets spread over many slices: block-parallel sum of their partials
-//   6. msm_reduce_level   sum_b (b+1) S_b by a radix-4..16 hierarchy: each level folds r consecutive buckets into a
-//                         weighted partial (running-sum trick) and a plain sum that feeds the next level;
-//      msm_reduce_direct  the last <= 4096 elements: weight applied by double-and-add
-//   7. msm_reduce_gather  all the partials of all levels summed under a per-thread Horner recurrence over the
-//      msm_reduce_final   levels (log2 r doublings each) -> one XYZZ per bucket set
+//   6. msm_reduce_level0  sum_b (b+1) S_b: chunks of 4-8 consecutive buckets -> plain sum U_q and weighted partial t_q
+//                         (running-sum trick, the only pass over all buckets)
+//   7. msm_tail_tasks     sum_q q U_q as plain column / row sums of the LO x HI arrangement of the chunks (one warp
+//      msm_tail_final     each, weight by double-and-add), then T + r0 (C + LO R) -> one XYZZ per bucket set
 //   8. msm_horner         raw flavour only: combine the windows (c doublings each)
 //   9. g1_finish          sum `count` partial points (count > 1 only for the multi-GPU gather), canonical affine
 // The result is a canonical group element, so it is byte-identical to the reference's regardless of window
@@ -212,17 +211,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, 
                                                                       uint32_t slice, const uint32_t* __restrict__ tile_sums,
                                                                       uint32_t* __restrict__ out, uint32_t* __restrict__ cursor,
                                                                       uint32_t* __restrict__ heavy,
-                                                                      uint32_t* __restrict__ heavy_count) {
+                                                                      uint32_t* __restrict__ heavy_count,
+                                                                      uint32_t* __restrict__ multi,
+                                                                      uint32_t* __restrict__ multi_count) {
     __shared__ uint32_t sh[SCAN_THREADS / 32];
+    __shared__ uint32_t multi_base;
     // thread owns SCAN_PER_THREAD consecutive keys so that its partial results are a running sum
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
     uint32_t val[SCAN_PER_THREAD];
-    uint32_t acc = 0;
+    uint32_t acc = 0, nmulti = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         uint32_t i = base + k;
         val[k] = i < nkeys ? scan_input(mode, counts, offsets, i, slice) : 0;
         acc += val[k];
+        nmulti += (val[k] >= 2 && val[k] <= HEAVY_PARTS) ? 1u : 0u;
     }
     uint32_t tot;
     uint32_t inc = block_scan_u32(acc, sh, tot);
@@ -236,6 +239,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, 
             if (mode == 1 && val[k] > HEAVY_PARTS) heavy[atomicAdd(heavy_count, 1u)] = i;
             run += val[k];
         }
+    }
+    if (mode == 1) {
+        // buckets with 2..HEAVY_PARTS partial sums: compact list (one atomic per block), folded by msm_fold_kernel
+        uint32_t mtot;
+        uint32_t minc = block_scan_u32(nmulti, sh, mtot);
+        if (threadIdx.x == 0) multi_base = mtot ? atomicAdd(multi_count, mtot) : 0u;
+        __syncthreads();
+        uint32_t pos = multi_base + minc - nmulti;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; k++)
+            if (val[k] >= 2 && val[k] <= HEAVY_PARTS) multi[pos++] = base + k;
     }
 }
 
@@ -318,6 +332,41 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
     store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
 }
 
+// The kernels after the accumulation are latency-bound (few warps, long dependent chains) and run once per MSM, so
+// their instructions come cold out of L2/DRAM: they all CALL one shared copy of the 14-product addition and of the
+// doubling instead of inlining ~60 KB of straight-line code at every use.
+__device__ __noinline__ void xyzz_add_fn(G1XYZZ& acc, const G1XYZZ& b) { xyzz_add(acc, b); }
+__device__ __noinline__ void xyzz_dbl_fn(G1XYZZ& p) { p = xyzz_dbl(p); }
+__device__ G1XYZZ xyzz_mul_small_fn(const G1XYZZ& p, uint32_t k) {
+    G1XYZZ r = xyzz_inf();
+    int top = 31;
+    while (top >= 0 && !((k >> top) & 1)) top--;
+#pragma unroll 1
+    for (int bit = top; bit >= 0; bit--) {
+        xyzz_dbl_fn(r);
+        if ((k >> bit) & 1) xyzz_add_fn(r, p);
+    }
+    return r;
+}
+
+// Buckets cut by slice boundaries hold 2..HEAVY_PARTS partial sums (about one bucket in two): one thread per such
+// bucket folds them into the first slot, so that the reduction reads exactly one point per bucket, divergence-free.
+__global__ void __launch_bounds__(128) msm_fold_kernel(G1XYZZ* __restrict__ partials, const uint32_t* __restrict__ pbase,
+                                                       const uint32_t* __restrict__ multi,
+                                                       const uint32_t* __restrict__ multi_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *multi_count) return;
+    const uint32_t key = multi[i];
+    const uint32_t a = pbase[key], b = pbase[key + 1];
+    G1XYZZ v = load_xyzz(partials + a);
+#pragma unroll 1
+    for (uint32_t j = a + 1; j < b; j++) {
+        G1XYZZ o = load_xyzz(partials + j);
+        xyzz_add(v, o);
+    }
+    store_xyzz(partials + a, v);
+}
+
 // A bucket that spans many slices holds many partial sums: one block per such bucket tree-sums them in shared
 // memory and leaves the total in the bucket's first slot.  (Buckets with <= HEAVY_PARTS partials are summed by
 // the reader, load_bucket.)
@@ -331,7 +380,7 @@ __device__ __forceinline__ void block_tree_sum(G1XYZZ& v, G1XYZZ* sh) {
         if (tid < s) {
             G1XYZZ a = load_xyzz(sh + tid);
             G1XYZZ b = load_xyzz(sh + tid + s);
-            xyzz_add(a, b);
+            xyzz_add_fn(a, b);
             store_xyzz(sh + tid, a);
         }
         __syncthreads();
@@ -352,7 +401,7 @@ __global__ void __launch_bounds__(RED_THREADS) msm_collapse_kernel(G1XYZZ* __res
         G1XYZZ v = xyzz_inf();
         for (uint32_t j = a + threadIdx.x; j < b; j += RED_THREADS) {
             G1XYZZ o = load_xyzz(partials + j);
-            xyzz_add(v, o);
+            xyzz_add_fn(v, o);
         }
         block_tree_sum(v, sh);
         if (threadIdx.x == 0) store_xyzz(partials + a, v);
@@ -360,42 +409,39 @@ __global__ void __launch_bounds__(RED_THREADS) msm_collapse_kernel(G1XYZZ* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// bucket reduction: per set  sum_{b < B} (b+1) S_b  as a hierarchy of radix-2^k levels.
-// With b = r q + j (r = 2^k):  (b+1) S_b = (j+1) S_b + r q S_b, so one level computes, per chunk q of r buckets,
-//   t_q = sum_j (j+1) S_{rq+j}   (running-sum trick; block-summed into `level_partials`)
-//   U_q = sum_j S_{rq+j}         (written out: the next level reduces sum_q q U_q = sum_{b'} (b'+1) U_{b'+1})
-// and  total = T_0 + r_0 (T_1 + r_1 (T_2 + ...)),  T_L = sum_q t_q at level L.  The radix of a level is chosen to
-// keep about 2^17 threads busy (the serial depth of a level is 2 r additions), the last few thousand elements are
-// finished by the direct kernel (weight q applied by double-and-add, log depth).
+// bucket reduction: per set  sum_{b < B} (b+1) S_b  in three launches whose serial depth does not grow with B.
+//   level 0   one thread per chunk q of r0 = 2^k0 consecutive buckets (the only pass over all the buckets, pipe-bound):
+//               U_q = sum_j S_{r0 q + j}                 (plain)
+//               t_q = sum_j (j+1) S_{r0 q + j}           (running-sum trick: 2 additions per bucket)
+//             so that  sum_b (b+1) S_b = sum_q t_q + r0 sum_q q U_q.
+//   tail      q = hi LO + lo with LO = 2^a ~ sqrt(n1):   sum_q q U_q = sum_lo lo C_lo + LO sum_hi hi R_hi
+//             where the column sums C_lo and the row sums R_hi are PLAIN sums -- no serial weighted recurrence left.
+//             msm_tail_tasks: one warp per column / row / run of LO t-values: lane-serial partial sums, a shuffle
+//             tree, then the weight (< 2^a) by double-and-add on lane 0.
+//             msm_tail_final: one block per set adds the three groups and forms  T + r0 (C + LO R).
+// Every step of the tail is latency-bound (one XYZZ addition is ~5 us for a lone warp), so what counts is the number
+// of dependent additions: ~20 per tail launch, against ~65 for a radix-4 hierarchy of running sums.
 // ---------------------------------------------------------------------------------------------
 
-// level 0 reads the accumulate output through pbase (summing the <= HEAVY_PARTS partials of a bucket); higher
-// levels read a dense array whose element 0 carries weight 0 and is skipped (shift = 1).  No block-level sum here:
-// the per-thread t_q are written out and msm_reduce_gather adds them all in one go (a tree sum per level would
-// put 7 more serial additions on the critical path of every level).
-__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_level_kernel(const G1XYZZ* __restrict__ in,
-                                                                          const uint32_t* __restrict__ pbase,
-                                                                          uint32_t n_in, uint32_t in_stride, uint32_t shift,
-                                                                          uint32_t radix, G1XYZZ* __restrict__ out_u,
-                                                                          uint32_t n_out, G1XYZZ* __restrict__ out_t) {
+// level 0 reads the accumulate output through pbase: one point per bucket (msm_fold / msm_collapse have folded the
+// partial sums of a bucket into its first slot), none for an empty bucket
+__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_level0_kernel(const G1XYZZ* __restrict__ in,
+                                                                           const uint32_t* __restrict__ pbase,
+                                                                           uint32_t nbuckets, uint32_t radix,
+                                                                           G1XYZZ* __restrict__ out_u, uint32_t n_out,
+                                                                           G1XYZZ* __restrict__ out_t) {
     const uint32_t set = blockIdx.y;
     const uint32_t q = blockIdx.x * RED_THREADS + threadIdx.x;
     if (q >= n_out) return;
     const uint32_t lo = q * radix;
-    const uint32_t hi = min(lo + radix, n_in);
+    const uint32_t hi = min(lo + radix, nbuckets);
     G1XYZZ run = xyzz_inf(), tot = xyzz_inf();
+#pragma unroll 1
     for (uint32_t b = hi; b-- > lo;) {
-        if (pbase) {
-            const uint32_t key = set * in_stride + b;
-            const uint32_t a = pbase[key];
-            uint32_t nparts = pbase[key + 1] - a;
-            if (nparts > HEAVY_PARTS) nparts = 1;  // collapsed into the first slot
-            for (uint32_t j = 0; j < nparts; j++) {
-                G1XYZZ o = load_xyzz(in + a + j);
-                xyzz_add(run, o);
-            }
-        } else {
-            G1XYZZ o = load_xyzz(in + (size_t)set * in_stride + b + shift);
+        const uint32_t key = set * nbuckets + b;
+        const uint32_t a = pbase[key];
+        if (pbase[key + 1] != a) {
+            G1XYZZ o = load_xyzz(in + a);
             xyzz_add(run, o);
         }
         xyzz_add(tot, run);
@@ -404,68 +450,139 @@ __global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_level_kernel(const 
     store_xyzz(out_t + (size_t)set * n_out + q, tot);
 }
 
-// Tail of the hierarchy: every thread scales its element by its weight q (double-and-add, <= 12 bits).
-constexpr uint32_t RED_DIRECT_MAX = 4096;
-__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_direct_kernel(const G1XYZZ* __restrict__ in, uint32_t n_in,
-                                                                           G1XYZZ* __restrict__ out_t) {
-    const uint32_t set = blockIdx.y;
-    const uint32_t q = blockIdx.x * RED_THREADS + threadIdx.x;
-    if (q >= n_in) return;
-    G1XYZZ v = xyzz_inf();
-    if (q >= 1) v = xyzz_mul_small(load_xyzz(in + (size_t)set * n_in + q), q);
-    store_xyzz(out_t + (size_t)set * n_in + q, v);
-}
-
-constexpr int RED_MAX_LEVELS = 12;
-struct RedLevels {
-    uint32_t nlevels;
-    uint32_t count[RED_MAX_LEVELS];       // t values per set at each level
-    uint32_t offset[RED_MAX_LEVELS];      // start of the level inside the t array (per-set runs contiguous)
-    uint32_t log_radix[RED_MAX_LEVELS];
-    uint32_t direct_count, direct_offset;  // values of the direct tail (0: none)
+struct TailGeom {
+    uint32_t n1;      // chunks per set after level 0
+    uint32_t k0;      // log2 of the level-0 radix
+    uint32_t log_lo;  // a
+    uint32_t lo, hi;  // LO = 2^a columns, HI = ceil(n1 / LO) rows
+    uint32_t ntask;   // LO column tasks, HI row tasks, HI runs of t-values
 };
 
-// grid = (G, nsets).  Every thread folds its strided share of each level's t values while running the Horner
-// recurrence over the levels ON ITS OWN share (the recurrence is linear, so the sum over all threads of the
-// per-thread results is the result); one tree sum per block.  With G == 1 the block's sum is the set's sum.
-__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_gather_kernel(const G1XYZZ* __restrict__ tvals, RedLevels lv,
-                                                                           uint32_t nsets, G1XYZZ* __restrict__ out) {
-    __shared__ G1XYZZ sh[RED_THREADS];
-    const uint32_t set = blockIdx.y;
-    const uint32_t g = blockIdx.x * RED_THREADS + threadIdx.x, stride = gridDim.x * RED_THREADS;
-    G1XYZZ acc = xyzz_inf();
-    if (lv.direct_count) {
-        const G1XYZZ* base = tvals + lv.direct_offset + (size_t)set * lv.direct_count;
-        for (uint32_t j = g; j < lv.direct_count; j += stride) {
-            G1XYZZ o = load_xyzz(base + j);
-            xyzz_add(acc, o);
-        }
-    }
-    for (int L = (int)lv.nlevels - 1; L >= 0; L--) {
+__device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, uint32_t d) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], d);
+    return r;
+}
+// Points in quad form (ec.cuh): lane j of every group of four lanes holds coordinate j.  All-reduce over the
+// quads whose lane indices differ in the bits [4, top]: afterwards each of them holds the sum.
+__device__ __forceinline__ void quad_butterfly(Fq& acc, uint32_t top, uint32_t j, uint32_t qm) {
+    __syncwarp();
 #pragma unroll 1
-        for (uint32_t k = 0; k < lv.log_radix[L]; k++) acc = xyzz_dbl(acc);
-        const G1XYZZ* base = tvals + lv.offset[L] + (size_t)set * lv.count[L];
-        for (uint32_t j = g; j < lv.count[L]; j += stride) {
-            G1XYZZ o = load_xyzz(base + j);
-            xyzz_add(acc, o);
-        }
+    for (uint32_t d = top; d >= 4; d >>= 1) {
+        const Fq o = shfl_xor_fq(acc, d);
+        quad_add(acc, o, j, qm);
     }
-    block_tree_sum(acc, sh);
-    if (threadIdx.x == 0) store_xyzz(out + (size_t)set * gridDim.x + blockIdx.x, acc);
 }
 
-// grid = nsets: sum of the `count` per-block results of the gather
-__global__ void __launch_bounds__(RED_THREADS, 3) msm_reduce_final_kernel(const G1XYZZ* __restrict__ parts, uint32_t count,
-                                                                          G1XYZZ* __restrict__ set_sums) {
-    __shared__ G1XYZZ sh[RED_THREADS];
-    const uint32_t set = blockIdx.x;
-    G1XYZZ acc = xyzz_inf();
-    for (uint32_t j = threadIdx.x; j < count; j += RED_THREADS) {
-        G1XYZZ o = load_xyzz(parts + (size_t)set * count + j);
-        xyzz_add(acc, o);
+// one block (32 quads) per task: a column, a row or a run of t-values
+constexpr int TAIL_THREADS = 128;
+__global__ void __launch_bounds__(TAIL_THREADS) msm_tail_tasks_kernel(const G1XYZZ* __restrict__ u,
+                                                                      const G1XYZZ* __restrict__ t, TailGeom tg,
+                                                                      G1XYZZ* __restrict__ w) {
+    __shared__ G1XYZZ sh[TAIL_THREADS / 32];
+    const uint32_t set = blockIdx.y, task = blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t j = threadIdx.x & 3, quad = threadIdx.x >> 2;
+    const uint32_t qm = quad_mask();
+    const G1XYZZ* src;
+    uint32_t first, step, count, weight;
+    if (task < tg.lo) {  // column `task`: q = hi LO + task
+        src = u + (size_t)set * tg.n1;
+        first = task;
+        step = tg.lo;
+        count = tg.n1 > task ? (tg.n1 - task + tg.lo - 1) >> tg.log_lo : 0u;
+        weight = task;
+    } else if (task < tg.lo + tg.hi) {  // row
+        const uint32_t h = task - tg.lo;
+        src = u + (size_t)set * tg.n1;
+        first = h << tg.log_lo;
+        step = 1;
+        count = min(tg.lo, tg.n1 - first);
+        weight = h;
+    } else {  // run of t-values
+        const uint32_t r = task - tg.lo - tg.hi;
+        src = t + (size_t)set * tg.n1;
+        first = r << tg.log_lo;
+        step = 1;
+        count = min(tg.lo, tg.n1 - first);
+        weight = 1;
     }
-    block_tree_sum(acc, sh);
-    if (threadIdx.x == 0) store_xyzz(set_sums + set, acc);
+    G1XYZZ* dst = w + (size_t)set * tg.ntask + task;
+    if (weight == 0) {  // (block-uniform) column 0 and row 0 carry weight 0
+        if (threadIdx.x < 4) quad_store(dst, j, fp_zero<FqP>());
+        return;
+    }
+    Fq acc = fp_zero<FqP>();
+#pragma unroll 1
+    for (uint32_t k = quad; k < count; k += TAIL_THREADS / 4) {
+        const Fq b = quad_load(src + first + (size_t)k * step, j);
+        quad_add(acc, b, j, qm);
+    }
+    quad_butterfly(acc, 16, j, qm);
+    if (lane < 4) quad_store(sh + warp, j, acc);
+    __syncthreads();
+    if (warp == 0) {
+        Fq v = quad < TAIL_THREADS / 32 ? quad_load(sh + quad, j) : fp_zero<FqP>();
+        quad_butterfly(v, TAIL_THREADS / 32 * 2, j, qm);  // quads 0..3 <-> lane bits 2..3: distances 8 and 4
+        if (quad == 0) {
+            if (weight > 1) quad_mul_small(v, weight, j, qm);
+            quad_store(dst, j, v);
+        }
+    }
+}
+
+// one block per set: warps 0-2 add the column results, 3-5 the row results, 6-7 the t results
+__global__ void __launch_bounds__(256) msm_tail_final_kernel(const G1XYZZ* __restrict__ w, TailGeom tg,
+                                                             G1XYZZ* __restrict__ set_sums) {
+    __shared__ G1XYZZ sh[8];
+    const uint32_t set = blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = threadIdx.x & 3;
+    const uint32_t qm = quad_mask();
+    uint32_t first, count, nw, rank;
+    if (warp < 3) {
+        first = 0; count = tg.lo; nw = 3; rank = warp;
+    } else if (warp < 6) {
+        first = tg.lo; count = tg.hi; nw = 3; rank = warp - 3;
+    } else {
+        first = tg.lo + tg.hi; count = tg.hi; nw = 2; rank = warp - 6;
+    }
+    const G1XYZZ* src = w + (size_t)set * tg.ntask + first;
+    Fq acc = fp_zero<FqP>();
+#pragma unroll 1
+    for (uint32_t k = rank * 8 + (lane >> 2); k < count; k += nw * 8) {
+        const Fq b = quad_load(src + k, j);
+        quad_add(acc, b, j, qm);
+    }
+    quad_butterfly(acc, 16, j, qm);
+    if (lane < 4) quad_store(sh + warp, j, acc);
+    __syncthreads();
+    // the three group totals on the first quad of three different warps: C, 2^a R, T
+    if (lane < 4 && warp < 3) {
+        const uint32_t base = warp * 3, n = warp == 2 ? 2u : 3u;
+        Fq v = quad_load(sh + base, j);
+#pragma unroll 1
+        for (uint32_t k = 1; k < n; k++) {
+            const Fq o = quad_load(sh + base + k, j);
+            quad_add(v, o, j, qm);
+        }
+        if (warp == 1) {
+#pragma unroll 1
+            for (uint32_t k = 0; k < tg.log_lo; k++) quad_dbl(v, j, qm);
+        }
+        quad_store(sh + base, j, v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        Fq v = quad_load(sh + 3, j);
+        Fq o = quad_load(sh + 0, j);
+        quad_add(v, o, j, qm);
+#pragma unroll 1
+        for (uint32_t k = 0; k < tg.k0; k++) quad_dbl(v, j, qm);
+        o = quad_load(sh + 6, j);
+        quad_add(v, o, j, qm);
+        quad_store(set_sums + set, j, v);
+    }
 }
 
 // result = sum_w 2^(c*w) * windows[w]   (raw flavour)
@@ -632,42 +749,19 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const uint64_t max_tasks = (max_entries + slice - 1) / slice;
     const uint64_t max_parts = max_tasks + nkeys + 1;
 
-    // reduction hierarchy
-    RedLevels lv;
-    memset(&lv, 0, sizeof(lv));
-    uint32_t n_in[RED_MAX_LEVELS], n_out[RED_MAX_LEVELS];
-    uint32_t t_total = 0;   // per-thread t values over all levels and sets
-    size_t u_total = 0;
-    {
-        uint32_t cur = g.nbuckets;  // weighted elements at this level
-        while (true) {
-            const uint32_t L = lv.nlevels;
-            // radix 4..16: keep ~2^17 threads per level across the sets
-            uint32_t lr = 2;
-            while (lr < 4 && ((uint64_t)cur * g.nsets >> (lr + 1)) >= (1u << 17)) lr++;
-            n_in[L] = cur;
-            n_out[L] = (cur + (1u << lr) - 1) >> lr;
-            lv.log_radix[L] = lr;
-            lv.count[L] = n_out[L];
-            lv.offset[L] = t_total;
-            t_total += n_out[L] * g.nsets;
-            u_total += (size_t)n_out[L] * g.nsets;
-            lv.nlevels++;
-            if (n_out[L] <= 1) break;
-            if (n_out[L] <= RED_DIRECT_MAX || lv.nlevels == RED_MAX_LEVELS) {
-                lv.direct_count = n_out[L];
-                lv.direct_offset = t_total;
-                t_total += lv.direct_count * g.nsets;
-                break;
-            }
-            cur = n_out[L] - 1;  // element 0 of the next level has weight 0
-        }
-    }
-    // gather blocks per set: ~8 values per thread, at most 256 blocks
-    uint32_t gather_blocks = (t_total / g.nsets + RED_THREADS * 8 - 1) / (RED_THREADS * 8);
-    if (gather_blocks < 1) gather_blocks = 1;
-    if (gather_blocks > 256) gather_blocks = 256;
-    const uint32_t part_total = gather_blocks * g.nsets;
+    // bucket reduction geometry: level-0 radix (enough chunks to keep every SM sub-partition busy), then the
+    // LO x HI shape of the tail
+    TailGeom tg;
+    tg.k0 = (uint64_t)g.nbuckets * g.nsets >= (1u << 19) ? 3 : 2;
+    if (const char* ov = getenv("KZGB200_RED_K0")) tg.k0 = (uint32_t)atoi(ov);  // tuning
+    if (tg.k0 > 6) tg.k0 = 6;
+    while (tg.k0 > 0 && (1u << tg.k0) > g.nbuckets) tg.k0--;
+    tg.n1 = (g.nbuckets + (1u << tg.k0) - 1) >> tg.k0;
+    tg.log_lo = 0;
+    while ((1ull << (2 * tg.log_lo)) < tg.n1) tg.log_lo++;
+    tg.lo = 1u << tg.log_lo;
+    tg.hi = (tg.n1 + tg.lo - 1) >> tg.log_lo;
+    tg.ntask = tg.lo + 2 * tg.hi;
 
     // scratch layout
     size_t off = 0;
@@ -677,13 +771,14 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const size_t o_segoff = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_sorted = off;   off = align_up(off + sizeof(uint32_t) * max_entries, 256);
     const size_t o_partials = off; off = align_up(off + sizeof(G1XYZZ) * max_parts, 256);
-    const size_t o_u = off;        off = align_up(off + sizeof(G1XYZZ) * u_total, 256);
-    const size_t o_tv = off;       off = align_up(off + sizeof(G1XYZZ) * t_total, 256);
-    const size_t o_lp = off;       off = align_up(off + sizeof(G1XYZZ) * part_total, 256);
+    const size_t o_u = off;        off = align_up(off + sizeof(G1XYZZ) * tg.n1 * g.nsets, 256);
+    const size_t o_tv = off;       off = align_up(off + sizeof(G1XYZZ) * tg.n1 * g.nsets, 256);
+    const size_t o_lp = off;       off = align_up(off + sizeof(G1XYZZ) * tg.ntask * g.nsets, 256);
     const size_t o_sets = off;     off = align_up(off + sizeof(G1XYZZ) * g.nsets, 256);
     const uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
     const size_t o_tiles = off;    off = align_up(off + sizeof(uint32_t) * ntiles, 256);
     const size_t o_heavy = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
+    const size_t o_multi = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     void* base = nullptr;
     KZG_TRY(ctx_scratch(ctx, off, &base));
     uint8_t* sc = (uint8_t*)base;
@@ -695,25 +790,27 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     G1XYZZ* partials = (G1XYZZ*)(sc + o_partials);
     G1XYZZ* u_arrays = (G1XYZZ*)(sc + o_u);
     G1XYZZ* tvals = (G1XYZZ*)(sc + o_tv);
-    G1XYZZ* gather_parts = (G1XYZZ*)(sc + o_lp);
+    G1XYZZ* tail_parts = (G1XYZZ*)(sc + o_lp);
     G1XYZZ* set_sums = (G1XYZZ*)(sc + o_sets);
     uint32_t* tile_sums = (uint32_t*)(sc + o_tiles);
     uint32_t* heavy = (uint32_t*)(sc + o_heavy);  // [0] = count, [1..] = keys
+    uint32_t* multi = (uint32_t*)(sc + o_multi);  // same layout: buckets with 2..HEAVY_PARTS partial sums
 
     const G1Affine* pts = bases.table ? bases.table : bases.pts;
     KZG_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nkeys + 1), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), ctx->stream));
+    KZG_CUDA(ctx, cudaMemsetAsync(multi, 0, sizeof(uint32_t), ctx->stream));
     const uint32_t dblocks = (uint32_t)((n + 255) / 256);
     timed_begin(ctx, KZG_TIMED_MSM_SORT);
     KZG_LAUNCH(ctx, msm_digits_kernel<false>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, counts, nullptr);
     KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums);
     KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, offsets);
     KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums,
-               offsets, cursor, heavy + 1, heavy);
+               offsets, cursor, heavy + 1, heavy, multi + 1, multi);
     KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums);
     KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, segoff);
     KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums, segoff, cursor,
-               heavy + 1, heavy);
+               heavy + 1, heavy, multi + 1, multi);
     KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
     timed_end(ctx, KZG_TIMED_MSM_SORT);
 
@@ -724,29 +821,15 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     timed_begin(ctx, KZG_TIMED_MSM_REDUCE);
     KZG_LAUNCH(ctx, msm_collapse_kernel, (uint32_t)ctx->sm_count * 2, RED_THREADS, 0, partials, segoff, heavy + 1, heavy);
     {
-        const G1XYZZ* in = partials;
-        G1XYZZ* u = u_arrays;
-        for (uint32_t L = 0; L < lv.nlevels; L++) {
-            const uint32_t blocks = (n_out[L] + RED_THREADS - 1) / RED_THREADS;
-            KZG_LAUNCH(ctx, msm_reduce_level_kernel, dim3(blocks, g.nsets), RED_THREADS, 0, in, L == 0 ? segoff : nullptr,
-                       n_in[L], L == 0 ? g.nbuckets : n_out[L - 1], L == 0 ? 0u : 1u, 1u << lv.log_radix[L], u, n_out[L],
-                       tvals + lv.offset[L]);
-            in = u;
-            u += (size_t)n_out[L] * g.nsets;
-        }
-        if (lv.direct_count) {
-            const uint32_t blocks = (lv.direct_count + RED_THREADS - 1) / RED_THREADS;
-            KZG_LAUNCH(ctx, msm_reduce_direct_kernel, dim3(blocks, g.nsets), RED_THREADS, 0, in, lv.direct_count,
-                       tvals + lv.direct_offset);
-        }
+        // every multi-part bucket contains a slice boundary: at most max_tasks of them
+        const uint64_t max_multi = max_tasks < nkeys ? max_tasks : nkeys;
+        KZG_LAUNCH(ctx, msm_fold_kernel, (uint32_t)((max_multi + 127) / 128), 128, 0, partials, segoff, multi + 1, multi);
     }
     G1XYZZ* sums_out = g.nsets == 1 ? result_dev : set_sums;
-    if (gather_blocks == 1) {
-        KZG_LAUNCH(ctx, msm_reduce_gather_kernel, dim3(1, g.nsets), RED_THREADS, 0, tvals, lv, g.nsets, sums_out);
-    } else {
-        KZG_LAUNCH(ctx, msm_reduce_gather_kernel, dim3(gather_blocks, g.nsets), RED_THREADS, 0, tvals, lv, g.nsets, gather_parts);
-        KZG_LAUNCH(ctx, msm_reduce_final_kernel, g.nsets, RED_THREADS, 0, gather_parts, gather_blocks, sums_out);
-    }
+    KZG_LAUNCH(ctx, msm_reduce_level0_kernel, dim3((tg.n1 + RED_THREADS - 1) / RED_THREADS, g.nsets), RED_THREADS, 0, partials,
+               segoff, g.nbuckets, 1u << tg.k0, u_arrays, tg.n1, tvals);
+    KZG_LAUNCH(ctx, msm_tail_tasks_kernel, dim3(tg.ntask, g.nsets), TAIL_THREADS, 0, u_arrays, tvals, tg, tail_parts);
+    KZG_LAUNCH(ctx, msm_tail_final_kernel, g.nsets, 256, 0, tail_parts, tg, sums_out);
     if (g.nsets > 1) KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, result_dev);
     timed_end(ctx, KZG_TIMED_MSM_REDUCE);
 #ifdef KZG_MSM_EXPERIMENT
