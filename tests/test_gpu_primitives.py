@@ -392,3 +392,31 @@ def test_srs_table_edge_cases(curve):
                 assert bytes(out) == bn.g1_to_bytes(bn.g1_mul_gen(expect)), (table_c, scalars[0])
     finally:
         curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+@pytest.mark.parametrize("table_c", [2, 3, 4, 6, 7, 9, 10, 12, 14, 15, 17])
+def test_msm_reduction_geometries(curve, tau, table_c, monkeypatch):
+    """the bucket reduction (folded partials -> level 0 -> LO x HI tail in quad-lane arithmetic) for every shape of the
+    tail: bucket sets of 2 ... 2^16 buckets, every level-0 radix, sparse and dense buckets, skewed scalars"""
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200._lib import as_ptr
+    n = 1500
+    srs = C.c_void_p()
+    curve.check(curve.lib.kzg_srs_generate(curve.ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
+    try:
+        curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, table_c))
+        scal = synthetic.random_fr_std(4200 + table_c, n)
+        cases = [[sum(int(scal[i, j]) << (64 * j) for j in range(4)) for i in range(n)],
+                 [(i % 3) + 1 for i in range(n)],                       # three buckets hold everything
+                 [((1 << table_c) - 1) << (table_c * (i % 5)) for i in range(n)]]  # top digits: carries into the next window
+        for k0 in ("0", "1", "2", "3", "5"):
+            monkeypatch.setenv("KZGB200_RED_K0", k0)
+            for scalars in cases:
+                expect = sum(s * pow(tau, i, R) for i, s in enumerate(scalars)) % R
+                buf = curve.to_device(bn.fr_vec_to_std_bytes(scalars))
+                out = bytearray(64)
+                curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out)))
+                assert bytes(out) == bn.g1_to_bytes(bn.g1_mul_gen(expect)), (table_c, k0)
+    finally:
+        monkeypatch.delenv("KZGB200_RED_K0", raising=False)
+        curve.lib.kzg_srs_free(curve.ctx, srs)
