@@ -420,3 +420,40 @@ def test_msm_reduction_geometries(curve, tau, table_c, monkeypatch):
     finally:
         monkeypatch.delenv("KZGB200_RED_K0", raising=False)
         curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+@pytest.mark.parametrize("flavour,c", [("table", 4), ("table", 9), ("table", 13), ("table", 16), ("table", 20),
+                                        ("raw", 5), ("raw", 11), ("raw", 16)])
+def test_msm_partition_sort(curve, tau, flavour, c, monkeypatch):
+    """the two-level partition sort (shared-memory histograms; the path of every MSM above ~2^16 points), forced on at a
+    size the oracle can check: uniform, skewed (all entries in one bucket / one partition) and Montgomery-source scalars"""
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200._lib import as_ptr
+    n = 2600
+    srs = C.c_void_p()
+    curve.check(curve.lib.kzg_srs_generate(curve.ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
+    try:
+        if flavour == "table":
+            curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, c))
+        else:
+            curve.check(curve.lib.kzg_msm_set_window(curve.ctx, c))
+        scal = synthetic.random_fr_std(5100 + c, n)
+        cases = [[sum(int(scal[i, j]) << (64 * j) for j in range(4)) for i in range(n)],
+                 [5] * n, [0] * n, [R - 1 - (i % 2) for i in range(n)]]
+        for part_sort in ("1", "0"):
+            monkeypatch.setenv("KZGB200_PART_SORT", part_sort)
+            for scalars in cases:
+                expect = sum(s * pow(tau, i, R) for i, s in enumerate(scalars)) % R
+                want = bn.g1_to_bytes(bn.g1_mul_gen(expect))
+                buf = curve.to_device(bn.fr_vec_to_std_bytes(scalars))
+                out = bytearray(64)
+                curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out)))
+                assert bytes(out) == want, (flavour, c, part_sort, scalars[0])
+                # Montgomery source (commit of a polynomial): fp_from_mont fused into the digit kernels
+                mont = curve.to_device(bn.fr_vec_to_mont_bytes(scalars))
+                curve.check(curve.lib.kzg_commit(curve.ctx, srs, mont.handle, as_ptr(out)))
+                assert bytes(out) == want, (flavour, c, part_sort, "commit")
+    finally:
+        monkeypatch.delenv("KZGB200_PART_SORT", raising=False)
+        curve.check(curve.lib.kzg_msm_set_window(curve.ctx, 0))
+        curve.lib.kzg_srs_free(curve.ctx, srs)
