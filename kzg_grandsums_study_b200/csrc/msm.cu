@@ -213,7 +213,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, 
                                                                       uint32_t* __restrict__ heavy,
                                                                       uint32_t* __restrict__ heavy_count,
                                                                       uint32_t* __restrict__ multi,
-                                                                      uint32_t* __restrict__ multi_count) {
+                                                                      uint32_t* __restrict__ multi_count,
+                                                                      uint32_t* __restrict__ huge,
+                                                                      uint32_t* __restrict__ huge_count) {
     __shared__ uint32_t sh[SCAN_THREADS / 32];
     __shared__ uint32_t multi_base;
     // thread owns SCAN_PER_THREAD consecutive keys so that its partial results are a running sum
@@ -236,7 +238,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, 
         if (i < nkeys) {
             out[i] = run;
             if (mode == 0) cursor[i] = run;
-            if (mode == 1 && val[k] > HEAVY_PARTS) heavy[atomicAdd(heavy_count, 1u)] = i;
+            if (mode == 1 && val[k] > HEAVY_PARTS) {
+                if (val[k] > 256u) huge[atomicAdd(huge_count, 1u)] = i;  // HUGE_PARTS
+                else heavy[atomicAdd(heavy_count, 1u)] = i;
+            }
             run += val[k];
         }
     }
@@ -620,39 +625,79 @@ __global__ void __launch_bounds__(128) msm_fold_kernel(G1XYZZ* __restrict__ part
 // the reader, load_bucket.)
 constexpr int RED_THREADS = 128;
 
-__device__ __forceinline__ void block_tree_sum(G1XYZZ& v, G1XYZZ* sh) {
-    const uint32_t tid = threadIdx.x;
-    store_xyzz(sh + tid, v);
-    __syncthreads();
-    for (uint32_t s = RED_THREADS / 2; s > 0; s >>= 1) {
-        if (tid < s) {
-            G1XYZZ a = load_xyzz(sh + tid);
-            G1XYZZ b = load_xyzz(sh + tid + s);
-            xyzz_add_fn(a, b);
-            store_xyzz(sh + tid, a);
-        }
-        __syncthreads();
+__device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, uint32_t d) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], d);
+    return r;
+}
+// Points in quad form (ec.cuh): lane j of every group of four lanes holds coordinate j.  All-reduce over the
+// quads whose lane indices differ in the bits [4, top]: afterwards each of them holds the sum.
+__device__ __forceinline__ void quad_butterfly(Fq& acc, uint32_t top, uint32_t j, uint32_t qm) {
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t d = top; d >= 4; d >>= 1) {
+        const Fq o = shfl_xor_fq(acc, d);
+        quad_add(acc, o, j, qm);
     }
-    v = load_xyzz(sh);
-    __syncthreads();
 }
 
-__global__ void __launch_bounds__(RED_THREADS) msm_collapse_kernel(G1XYZZ* __restrict__ partials,
-                                                                   const uint32_t* __restrict__ pbase,
-                                                                   const uint32_t* __restrict__ heavy,
-                                                                   const uint32_t* __restrict__ heavy_count) {
-    __shared__ G1XYZZ sh[RED_THREADS];
+// Heavy buckets (more than HEAVY_PARTS partial sums: skewed scalars, or the short top window whose few digit values
+// each collect n / 2^bits points).  Their partial sums are contiguous, so this is a plain sum, done in quad-lane
+// arithmetic: one WARP per bucket up to HUGE_PARTS partials (8 quads stride over them, 3-level butterfly), one
+// 512-thread BLOCK (128 quads) per bucket beyond.  The total lands in the bucket's first slot.
+constexpr uint32_t HUGE_PARTS = 256;
+__global__ void __launch_bounds__(128) msm_collapse_kernel(G1XYZZ* __restrict__ partials, const uint32_t* __restrict__ pbase,
+                                                           const uint32_t* __restrict__ heavy,
+                                                           const uint32_t* __restrict__ heavy_count) {
     const uint32_t nheavy = *heavy_count;
-    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    const uint32_t lane = threadIdx.x & 31, j = threadIdx.x & 3;
+    const uint32_t qm = quad_mask();
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t h = gwarp; h < nheavy; h += nwarps) {
         const uint32_t key = heavy[h];
         const uint32_t a = pbase[key], b = pbase[key + 1];
-        G1XYZZ v = xyzz_inf();
-        for (uint32_t j = a + threadIdx.x; j < b; j += RED_THREADS) {
-            G1XYZZ o = load_xyzz(partials + j);
-            xyzz_add_fn(v, o);
+        Fq acc = fp_zero<FqP>();
+#pragma unroll 1
+        for (uint32_t k = a + (lane >> 2); k < b; k += 8) {
+            const Fq o = quad_load(partials + k, j);
+            quad_add(acc, o, j, qm);
         }
-        block_tree_sum(v, sh);
-        if (threadIdx.x == 0) store_xyzz(partials + a, v);
+        quad_butterfly(acc, 16, j, qm);  // (also orders every read of slot a before the write below)
+        if (lane < 4) quad_store(partials + a, j, acc);
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(512) msm_collapse_huge_kernel(G1XYZZ* __restrict__ partials, const uint32_t* __restrict__ pbase,
+                                                                 const uint32_t* __restrict__ huge,
+                                                                 const uint32_t* __restrict__ huge_count) {
+    __shared__ G1XYZZ sh[16];
+    const uint32_t nhuge = *huge_count;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = threadIdx.x & 3;
+    const uint32_t qm = quad_mask();
+    for (uint32_t h = blockIdx.x; h < nhuge; h += gridDim.x) {
+        const uint32_t key = huge[h];
+        const uint32_t a = pbase[key], b = pbase[key + 1];
+        Fq acc = fp_zero<FqP>();
+#pragma unroll 1
+        for (uint32_t k = a + (threadIdx.x >> 2); k < b; k += 128) {
+            const Fq o = quad_load(partials + k, j);
+            quad_add(acc, o, j, qm);
+        }
+        quad_butterfly(acc, 16, j, qm);
+        if (lane < 4) quad_store(sh + warp, j, acc);
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t q = lane >> 2;  // quad q adds the sums of warps q and q + 8
+            Fq v = quad_load(sh + q, j);
+            {
+                const Fq o = quad_load(sh + q + 8, j);
+                quad_add(v, o, j, qm);
+            }
+            quad_butterfly(v, 16, j, qm);
+            if (lane < 4) quad_store(partials + a, j, v);
+        }
+        __syncthreads();
     }
 }
 
@@ -705,23 +750,6 @@ struct TailGeom {
     uint32_t lo, hi;  // LO = 2^a columns, HI = ceil(n1 / LO) rows
     uint32_t ntask;   // LO column tasks, HI row tasks, HI runs of t-values
 };
-
-__device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, uint32_t d) {
-    Fq r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], d);
-    return r;
-}
-// Points in quad form (ec.cuh): lane j of every group of four lanes holds coordinate j.  All-reduce over the
-// quads whose lane indices differ in the bits [4, top]: afterwards each of them holds the sum.
-__device__ __forceinline__ void quad_butterfly(Fq& acc, uint32_t top, uint32_t j, uint32_t qm) {
-    __syncwarp();
-#pragma unroll 1
-    for (uint32_t d = top; d >= 4; d >>= 1) {
-        const Fq o = shfl_xor_fq(acc, d);
-        quad_add(acc, o, j, qm);
-    }
-}
 
 // one block (32 quads) per task: a column, a row or a run of t-values
 template <int TAIL_THREADS>
@@ -932,19 +960,33 @@ static uint32_t auto_window_raw(uint64_t n) {
     return (uint32_t)c;
 }
 
-// table flavour: one bucket set.  Cost model in units of one mixed addition:
+// table flavour: one bucket set.  Cost model in units of one mixed addition (0.16 ns at full pipe rate):
 //   n * digits(c)                 bucket accumulation
-//   x 1.12 if 2^(c-1) > 2^19      the counting-sort scatter keeps one partially written 128 B line per bucket; beyond
+//   x 1.12 if 2^(c-1) > 2^19      direct counting sort only: it keeps one partially written 128 B line per bucket; beyond
 //                                 ~64 MB of such lines they no longer fit the 126 MB L2 and every 4-byte store becomes a
-//                                 DRAM read-modify-write (measured: 6.3 ms instead of 2.5 ms at 2^24 points)
-//   + 3 * 2^(c-1)                 bucket reduction (~3 full additions per bucket)
+//                                 DRAM read-modify-write (measured: 6.3 ms instead of 2.5 ms at 2^24 points).  The
+//                                 partition sort (>= 2^27 entries) confines its stores to one partition's window.
+//   + 4.6 * 2^(c-1)               bucket reduction (measured: 0.64 ms at 2^19 buckets, 1.96 ms at 2^21, ~0.25 ms of it
+//                                 independent of the bucket count)
+constexpr uint64_t PART_SORT_MIN_ENTRIES = 1ull << 27;
 uint32_t msm_table_window(uint64_t n) {
     uint32_t best = 4;
     double best_cost = 1e300;
     for (uint32_t c = 4; c <= 23; c++) {
-        double cost = (double)n * windows_for(c, false);
-        if (c > 20) cost *= 1.12;
-        cost += 3.0 * (double)(1ull << (c - 1));
+        const double entries = (double)n * windows_for(c, false);
+        double cost = entries;
+        if (c > 20 && entries < (double)PART_SORT_MIN_ENTRIES) cost *= 1.12;
+        cost += 4.6 * (double)(1ull << (c - 1));
+        // a short top window (scalars are < 2^254) funnels n / 2^bits points into each of its few buckets: thousands of
+        // partial sums per bucket for the collapse kernels, hot addresses for the sort (measured: +0.3 ms at 2^18, c = 18)
+        const uint32_t top_bits = 254 - c * ((254 + c - 1) / c - 1);
+        double slice = 4.0 * (entries / (double)(1ull << (c - 1)) + 1.0);  // (as msm_run picks it)
+        if (slice > entries / 303104.0) slice = entries / 303104.0;
+        if (slice < 16) slice = 16;
+        if (slice > 512) slice = 512;
+        const double hot_parts = (double)(n >> top_bits) / slice;  // partial sums per bucket of the top window
+        if (hot_parts > 8.0 && entries < (double)PART_SORT_MIN_ENTRIES) cost += 0.1 * entries;  // hot addresses in the direct sort
+        if (hot_parts > 256.0) cost += 3.0e6;                      // block-tier collapse: ~50 dependent quad additions
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
@@ -1027,11 +1069,12 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const size_t o_tiles = off;    off = align_up(off + sizeof(uint32_t) * ntiles, 256);
     const size_t o_heavy = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_multi = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
+    const size_t o_huge = off;     off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     // partition sort (large inputs)
     SortGeom sg;
     memset(&sg, 0, sizeof(sg));
     // (measured on B200: ahead of the direct scheme only once the direct scatter's open lines overflow L2)
-    bool use_part_sort = max_entries >= (1ull << 27);
+    bool use_part_sort = max_entries >= PART_SORT_MIN_ENTRIES;
     if (const char* ov = getenv("KZGB200_PART_SORT")) use_part_sort = atoi(ov) != 0;  // tuning / A-B tests
     uint32_t max_chunks = 0;
     size_t o_mid = 0, o_phist = 0, o_pstart = 0, o_pcursor = 0, o_cstart = 0, o_chist = 0;
@@ -1076,6 +1119,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     uint32_t* tile_sums = (uint32_t*)(sc + o_tiles);
     uint32_t* heavy = (uint32_t*)(sc + o_heavy);  // [0] = count, [1..] = keys
     uint32_t* multi = (uint32_t*)(sc + o_multi);  // same layout: buckets with 2..HEAVY_PARTS partial sums
+    uint32_t* huge = (uint32_t*)(sc + o_huge);    // same layout: buckets with more than HUGE_PARTS partial sums
     uint2* mid = (uint2*)(sc + o_mid);
     uint32_t* part_hist = (uint32_t*)(sc + o_phist);
     uint32_t* pstart = (uint32_t*)(sc + o_pstart);
@@ -1087,6 +1131,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nkeys + 1), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(multi, 0, sizeof(uint32_t), ctx->stream));
+    KZG_CUDA(ctx, cudaMemsetAsync(huge, 0, sizeof(uint32_t), ctx->stream));
     const uint32_t dblocks = (uint32_t)((n + 255) / 256);
     timed_begin(ctx, KZG_TIMED_MSM_SORT);
     if (use_part_sort) {
@@ -1109,11 +1154,11 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums);
     KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, offsets);
     KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums,
-               offsets, cursor, heavy + 1, heavy, multi + 1, multi);
+               offsets, cursor, heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
     KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums);
     KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, segoff);
     KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums, segoff, cursor,
-               heavy + 1, heavy, multi + 1, multi);
+               heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
     if (use_part_sort)
         KZG_LAUNCH(ctx, msm_chunk_scatter_kernel, max_chunks, CHUNK_THREADS, 0, mid, pstart, cstart, sg, chunk_hist, cursor, sorted);
     else
@@ -1125,7 +1170,8 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_LAUNCH(ctx, msm_accumulate_kernel, ablocks, 128, 0, pts, sorted, offsets, segoff, nkeys, g.seg, partials);
     timed_end(ctx, KZG_TIMED_MSM_ACCUMULATE);
     timed_begin(ctx, KZG_TIMED_MSM_REDUCE);
-    KZG_LAUNCH(ctx, msm_collapse_kernel, (uint32_t)ctx->sm_count * 2, RED_THREADS, 0, partials, segoff, heavy + 1, heavy);
+    KZG_LAUNCH(ctx, msm_collapse_huge_kernel, 128, 512, 0, partials, segoff, huge + 1, huge);
+    KZG_LAUNCH(ctx, msm_collapse_kernel, (uint32_t)ctx->sm_count * 4, 128, 0, partials, segoff, heavy + 1, heavy);
     {
         // every multi-part bucket contains a slice boundary: at most max_tasks of them
         const uint64_t max_multi = max_tasks < nkeys ? max_tasks : nkeys;
@@ -1414,7 +1460,7 @@ int kzg_g1_partials_combine(kzg_ctx* ctx, const void* partials_dev, uint32_t cou
 }
 
 // scalars from host memory against a resident SRS (the e2e path of bench.py: H2D of the scalars is inside).
-// Large inputs are cut into three pieces of 1/8, 2/8 and 5/8 of the points: all the uploads are queued on the
+// Large inputs are cut into growing pieces (1/8, 2/8, 5/8 of the points): all the uploads are queued on the
 // auxiliary stream (copy engine) at once, and the MSM of piece k on the main stream waits only for ITS upload, so that
 // only the first, small upload is exposed and every later one hides behind the previous piece's MSM (each piece's MSM
 // takes longer than the next piece's upload at PCIe 5 x16 rates); the partial points are added by g1_finish.
@@ -1430,19 +1476,26 @@ int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* sca
     int r = KZG_OK;
     uint32_t parts = 1;
     if (n >= (1ull << 22)) {
+        // every piece pays the fixed part of an MSM again (~1.3 ms with 2^19 buckets, ~2.2 ms with the 2^21 buckets of a
+        // c = 22 table): three pieces of 1/8, 2/8, 5/8 for the former, two of 3/16, 13/16 for the latter
+        uint64_t cut[4] = {0, n / 8, n / 8 + n / 4, n};
         parts = 3;
-        const uint64_t cut[4] = {0, n / 8, n / 8 + n / 4, n};
+        if (srs->table && srs->tab_c > 20 && ctx->msm_window == 0) {
+            parts = 2;
+            cut[1] = n / 16 * 3;
+            cut[2] = n;
+        }
         cudaEvent_t up[3] = {nullptr, nullptr, nullptr};
-        for (int k = 0; k < 3; k++) cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming);
+        for (uint32_t k = 0; k < parts; k++) cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming);
         cudaError_t e = cudaEventRecord(ctx->ev_fork, ctx->stream);  // tmp exists from here on
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0);
-        for (int k = 0; k < 3 && e == cudaSuccess; k++) {
+        for (uint32_t k = 0; k < parts && e == cudaSuccess; k++) {
             e = cudaMemcpyAsync(tmp + cut[k], host + cut[k], sizeof(Fr) * (cut[k + 1] - cut[k]), cudaMemcpyHostToDevice,
                                 ctx->aux_stream);
             if (e == cudaSuccess) e = cudaEventRecord(up[k], ctx->aux_stream);
         }
         if (e != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, std::string("msm upload: ") + cudaGetErrorString(e));
-        for (int k = 0; k < 3 && r == KZG_OK; k++) {
+        for (uint32_t k = 0; k < parts && r == KZG_OK; k++) {
             cudaStreamWaitEvent(ctx->stream, up[k], 0);
             r = msm_run(ctx, srs_bases(ctx, srs, first + cut[k]), MsmScalarSrc{tmp + cut[k], false}, cut[k + 1] - cut[k], slots + k);
         }
@@ -1451,7 +1504,7 @@ int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* sca
         cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
         if (r == KZG_OK) r = msm_result_to_host_affine(ctx, slots, parts, out_affine);
         else cudaStreamSynchronize(ctx->stream);
-        for (int k = 0; k < 3; k++) cudaEventDestroy(up[k]);
+        for (uint32_t k = 0; k < parts; k++) cudaEventDestroy(up[k]);
     } else {
         if (n) KZG_CUDA(ctx, cudaMemcpyAsync(tmp, host, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
         r = msm_run(ctx, srs_bases(ctx, srs, first), MsmScalarSrc{tmp, false}, n, slots);

@@ -23,7 +23,7 @@ for log_n in sizes:
     n = 1 << log_n
     srs = C.c_void_p()
     curve.check(lib.kzg_srs_generate(ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
-    curve.check(lib.kzg_srs_precompute(ctx, srs, 0))
+    curve.check(lib.kzg_srs_precompute(ctx, srs, int(os.environ.get("TABLE_C", "0"))))
     scal = curve.to_device(synthetic.random_fr_std(6, n).tobytes())
     out = bytearray(64)
     wb, nw = C.c_uint32(), C.c_uint32()
