@@ -137,6 +137,7 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_PER_THREAD = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
 constexpr uint32_t HEAVY_PARTS = 8;
+constexpr uint32_t HUGE_PARTS = 256;
 
 __device__ __forceinline__ uint32_t parts_of(uint32_t off, uint32_t cnt, uint32_t slice) {
     return cnt == 0 ? 0u : (off + cnt - 1) / slice - off / slice + 1;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, 
             out[i] = run;
             if (mode == 0) cursor[i] = run;
             if (mode == 1 && val[k] > HEAVY_PARTS) {
-                if (val[k] > 256u) huge[atomicAdd(huge_count, 1u)] = i;  // HUGE_PARTS
+                if (val[k] > HUGE_PARTS) huge[atomicAdd(huge_count, 1u)] = i;
                 else heavy[atomicAdd(heavy_count, 1u)] = i;
             }
             run += val[k];
@@ -279,24 +280,29 @@ struct SortGeom {
     uint32_t tile_scalars;  // scalars per tile of kernels 1 and 3 (<= PART_THREADS * PART_ITEMS)
     uint32_t ntiles;
 };
-constexpr int PART_THREADS = 256;
-constexpr int PART_ITEMS = 4;
+constexpr int PART_THREADS = 512;
+constexpr int PART_ITEMS = 2;
 constexpr uint32_t PART_TILE_ENTRIES = 8192;   // 64 KB of staged pairs + 16 KB of ranks: two tiles per SM
 constexpr uint32_t SORT_MAX_PARTS = 2048;
 constexpr uint32_t SORT_MAX_LOW = 11;
-constexpr uint32_t SORT_CHUNK = 16384;
+constexpr uint32_t SORT_CHUNK = 8192;
 constexpr int CHUNK_THREADS = 512;
+constexpr size_t CHUNK_SMEM = sizeof(uint32_t) * (SORT_CHUNK + 3 * (1u << SORT_MAX_LOW) + 1) + sizeof(uint16_t) * SORT_CHUNK;
 
+// signed c-bit digits of a scalar, least significant first: a 64-bit bit buffer is refilled limb by limb (static limb
+// indices: the scalar stays in registers), the windows beyond bit 255 see zeros plus the carry
 template <class F>
 __device__ __forceinline__ void msm_for_digits(const Fr& s, const MsmGeom& g, uint64_t i, F&& f) {
-    uint32_t carry = 0;
-    const uint32_t half = g.nbuckets;
+    const uint32_t half = g.nbuckets, c = g.c, mask = (1u << g.c) - 1u;
     const bool table = g.nsets == 1;
-    for (uint32_t w = 0; w < g.nwin; w++) {
-        uint32_t raw = scalar_bits(s.l, w * g.c, g.c) + carry;
+    uint64_t buf = 0;
+    uint32_t have = 0, w = 0, carry = 0;
+    auto emit = [&]() {
+        const uint32_t raw = ((uint32_t)buf & mask) + carry;
+        buf >>= c;
         uint32_t mag, neg;
         if (raw > half) {
-            mag = (1u << g.c) - raw;
+            mag = (1u << c) - raw;
             neg = 1;
             carry = 1;
         } else {
@@ -305,11 +311,22 @@ __device__ __forceinline__ void msm_for_digits(const Fr& s, const MsmGeom& g, ui
             carry = 0;
         }
         if (mag != 0) {
-            const uint32_t key = (table ? 0u : w * g.nbuckets) + (mag - 1);
+            const uint32_t key = (table ? 0u : w * half) + (mag - 1);
             const uint32_t entry = table ? (uint32_t)(w * g.stride + i) : (uint32_t)i;
             f(key, entry | (neg << 31));
         }
+        w++;
+    };
+#pragma unroll
+    for (int limb = 0; limb < 8; limb++) {
+        buf |= (uint64_t)s.l[limb] << have;
+        have += 32;
+        while (have >= c && w < g.nwin) {
+            emit();
+            have -= c;
+        }
     }
+    while (w < g.nwin) emit();  // the last, partial window(s)
 }
 __device__ __forceinline__ Fr load_scalar_stream(const Fr* scalars, uint64_t i, bool montgomery) {
     Fr s;
@@ -371,16 +388,53 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_part_scan_kernel(const uint3
     }
 }
 
-__global__ void __launch_bounds__(PART_THREADS) msm_part_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, bool montgomery,
-                                                                        MsmGeom g, SortGeom sg, uint32_t* __restrict__ part_cursor,
-                                                                        uint2* __restrict__ mid) {
+// exclusive scan of cnt[0 .. n) (n <= THREADS * PER, in shared memory) into off[0 .. n], off[n] = total; every thread
+// of the block calls
+template <int THREADS, int PER>
+__device__ __forceinline__ void block_exclusive_scan_smem(const uint32_t* cnt, uint32_t* off, uint32_t n, uint32_t* warp_sums) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t base = threadIdx.x * PER;
+    uint32_t v[PER], acc = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        v[k] = base + k < n ? cnt[base + k] : 0u;
+        acc += v[k];
+    }
+    uint32_t inc = acc;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    uint32_t carry = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < THREADS / 32; k++) {
+        const uint32_t x = warp_sums[k];
+        if (k < (int)wid) carry += x;
+        tot += x;
+    }
+    uint32_t run = carry + inc - acc;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        if (base + k < n) off[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 0) off[n] = tot;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PART_THREADS, 2) msm_part_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, bool montgomery,
+                                                                           MsmGeom g, SortGeom sg, uint32_t* __restrict__ part_cursor,
+                                                                           uint2* __restrict__ mid) {
     extern __shared__ __align__(16) unsigned char part_smem[];
     uint2* stage = reinterpret_cast<uint2*>(part_smem);                                             // PART_TILE_ENTRIES pairs
     uint16_t* ranks = reinterpret_cast<uint16_t*>(part_smem + sizeof(uint2) * PART_TILE_ENTRIES);   // rank of every digit in its partition
     uint32_t* hist = reinterpret_cast<uint32_t*>(part_smem + (sizeof(uint2) + sizeof(uint16_t)) * PART_TILE_ENTRIES);
     uint32_t* loff = hist + sg.nparts;       // first staged slot of the partition (nparts + 1 values)
     uint32_t* gbase = loff + sg.nparts + 1;  // first slot in mid[]
-    __shared__ uint32_t sh[PART_THREADS / 32];
+    __shared__ uint32_t warp_sums[PART_THREADS / 32];
     for (uint32_t p = threadIdx.x; p < sg.nparts; p += PART_THREADS) hist[p] = 0;
     __syncthreads();
     const uint64_t first = (uint64_t)blockIdx.x * sg.tile_scalars;
@@ -399,29 +453,12 @@ __global__ void __launch_bounds__(PART_THREADS) msm_part_scatter_kernel(const Fr
         }
     }
     __syncthreads();
-    {
-        // exclusive scan of the partition counts (thread owns PER consecutive partitions); reserve the runs in mid[]
-        constexpr uint32_t PER = SORT_MAX_PARTS / PART_THREADS;
-        const uint32_t base = threadIdx.x * PER;
-        uint32_t cnt[PER], acc = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < PER; k++) {
-            cnt[k] = base + k < sg.nparts ? hist[base + k] : 0u;
-            acc += cnt[k];
-        }
-        uint32_t tot;
-        uint32_t run = block_scan_u32(acc, sh, tot) - acc;
-#pragma unroll
-        for (uint32_t k = 0; k < PER; k++) {
-            if (base + k < sg.nparts) {
-                loff[base + k] = run;
-                gbase[base + k] = cnt[k] ? atomicAdd(&part_cursor[base + k], cnt[k]) : 0u;
-            }
-            run += cnt[k];
-        }
-        if (threadIdx.x == 0) loff[sg.nparts] = tot;
+    block_exclusive_scan_smem<PART_THREADS, SORT_MAX_PARTS / PART_THREADS>(hist, loff, sg.nparts, warp_sums);
+    // reserve the runs in mid[]
+    for (uint32_t p = threadIdx.x; p < sg.nparts; p += PART_THREADS) {
+        const uint32_t cnt = hist[p];
+        gbase[p] = cnt ? atomicAdd(&part_cursor[p], cnt) : 0u;
     }
-    __syncthreads();
 #pragma unroll
     for (int k = 0; k < PART_ITEMS; k++) {
         const uint32_t local = threadIdx.x + k * PART_THREADS;
@@ -485,24 +522,42 @@ __global__ void __launch_bounds__(CHUNK_THREADS) msm_chunk_scatter_kernel(const 
                                                                           const uint16_t* __restrict__ chunk_hist,
                                                                           uint32_t* __restrict__ cursor,
                                                                           uint32_t* __restrict__ sorted) {
-    __shared__ uint32_t lc[1u << SORT_MAX_LOW];    // local cursors
-    __shared__ uint32_t base[1u << SORT_MAX_LOW];  // first slot in sorted[] for this chunk's entries of the key
+    // the chunk's payloads are staged in shared memory in key order and leave in runs (one run per key: a full
+    // 32-byte sector on average) instead of one scattered 4-byte store per entry
+    extern __shared__ __align__(16) unsigned char chunk_smem[];
+    uint32_t* stage = reinterpret_cast<uint32_t*>(chunk_smem);                 // SORT_CHUNK payloads
+    uint32_t* cnt = stage + SORT_CHUNK;                                        // counts, then local cursors
+    uint32_t* loff = cnt + (1u << SORT_MAX_LOW);                               // first staged slot of the key (+1)
+    uint32_t* base = loff + (1u << SORT_MAX_LOW) + 1;                          // first slot in sorted[] for this chunk's entries of the key
+    uint16_t* skey = reinterpret_cast<uint16_t*>(base + (1u << SORT_MAX_LOW)); // key of the staged payload
+    __shared__ uint32_t warp_sums[CHUNK_THREADS / 32];
     uint32_t part, begin, end;
     if (!chunk_range(pstart, cstart, sg.nparts, blockIdx.x, part, begin, end)) return;
     const uint32_t nlow = 1u << sg.low_bits, mask = nlow - 1;
     uint32_t* cur = cursor + ((size_t)part << sg.low_bits);
     const uint16_t* keep = chunk_hist + ((size_t)blockIdx.x << sg.low_bits);
     for (uint32_t k = threadIdx.x; k < nlow; k += CHUNK_THREADS) {
-        const uint32_t cnt = keep[k];
-        base[k] = cnt ? atomicAdd(&cur[k], cnt) : 0u;
-        lc[k] = 0;
+        const uint32_t c = keep[k];
+        cnt[k] = c;
+        base[k] = c ? atomicAdd(&cur[k], c) : 0u;
     }
+    __syncthreads();
+    block_exclusive_scan_smem<CHUNK_THREADS, (1 << SORT_MAX_LOW) / CHUNK_THREADS>(cnt, loff, nlow, warp_sums);
+    for (uint32_t k = threadIdx.x; k < nlow; k += CHUNK_THREADS) cnt[k] = 0;
     __syncthreads();
 #pragma unroll 4
     for (uint32_t e = begin + threadIdx.x; e < end; e += CHUNK_THREADS) {
         const uint2 v = __ldg(&mid[e]);
         const uint32_t k = v.y & mask;
-        sorted[base[k] + atomicAdd(&lc[k], 1u)] = v.x;
+        const uint32_t slot = loff[k] + atomicAdd(&cnt[k], 1u);
+        stage[slot] = v.x;
+        skey[slot] = (uint16_t)k;
+    }
+    __syncthreads();
+    const uint32_t total = end - begin;
+    for (uint32_t sidx = threadIdx.x; sidx < total; sidx += CHUNK_THREADS) {
+        const uint32_t k = skey[sidx];
+        sorted[base[k] + (sidx - loff[k])] = stage[sidx];
     }
 }
 
@@ -646,7 +701,6 @@ __device__ __forceinline__ void quad_butterfly(Fq& acc, uint32_t top, uint32_t j
 // each collect n / 2^bits points).  Their partial sums are contiguous, so this is a plain sum, done in quad-lane
 // arithmetic: one WARP per bucket up to HUGE_PARTS partials (8 quads stride over them, 3-level butterfly), one
 // 512-thread BLOCK (128 quads) per bucket beyond.  The total lands in the bucket's first slot.
-constexpr uint32_t HUGE_PARTS = 256;
 __global__ void __launch_bounds__(128) msm_collapse_kernel(G1XYZZ* __restrict__ partials, const uint32_t* __restrict__ pbase,
                                                            const uint32_t* __restrict__ heavy,
                                                            const uint32_t* __restrict__ heavy_count) {
@@ -968,7 +1022,7 @@ static uint32_t auto_window_raw(uint64_t n) {
 //                                 partition sort (>= 2^27 entries) confines its stores to one partition's window.
 //   + 4.6 * 2^(c-1)               bucket reduction (measured: 0.64 ms at 2^19 buckets, 1.96 ms at 2^21, ~0.25 ms of it
 //                                 independent of the bucket count)
-constexpr uint64_t PART_SORT_MIN_ENTRIES = 1ull << 27;
+constexpr uint64_t PART_SORT_MIN_ENTRIES = 1ull << 22;
 uint32_t msm_table_window(uint64_t n) {
     uint32_t best = 4;
     double best_cost = 1e300;
@@ -987,6 +1041,7 @@ uint32_t msm_table_window(uint64_t n) {
         const double hot_parts = (double)(n >> top_bits) / slice;  // partial sums per bucket of the top window
         if (hot_parts > 8.0 && entries < (double)PART_SORT_MIN_ENTRIES) cost += 0.1 * entries;  // hot addresses in the direct sort
         if (hot_parts > 256.0) cost += 3.0e6;                      // block-tier collapse: ~50 dependent quad additions
+        else if (hot_parts > 8.0) cost += (hot_parts / 8.0 + 3.0) * 15.6e3;  // warp tier: 2.5 us per dependent quad addition
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
@@ -1073,7 +1128,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     // partition sort (large inputs)
     SortGeom sg;
     memset(&sg, 0, sizeof(sg));
-    // (measured on B200: ahead of the direct scheme only once the direct scatter's open lines overflow L2)
+    // (measured on B200: 0.24 vs 0.32 ms at 2^20 points, 0.74 vs 1.11 ms at 2^22, 2.9 vs 5.7 ms at 2^24; level below 2^18)
     bool use_part_sort = max_entries >= PART_SORT_MIN_ENTRIES;
     if (const char* ov = getenv("KZGB200_PART_SORT")) use_part_sort = atoi(ov) != 0;  // tuning / A-B tests
     uint32_t max_chunks = 0;
@@ -1090,6 +1145,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         } else {
             sg.tile_scalars = PART_TILE_ENTRIES / g.nwin;
             if (sg.tile_scalars > PART_THREADS * PART_ITEMS) sg.tile_scalars = PART_THREADS * PART_ITEMS;
+            if (sg.tile_scalars > PART_THREADS) sg.tile_scalars = PART_THREADS;  // equal work per thread
             if (sg.tile_scalars == 0) use_part_sort = false;
         }
     }
@@ -1140,6 +1196,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         static bool attr_set[64] = {};
         if (!attr_set[ctx->device & 63]) {
             KZG_CUDA(ctx, cudaFuncSetAttribute(msm_part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_max));
+            KZG_CUDA(ctx, cudaFuncSetAttribute(msm_chunk_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHUNK_SMEM));
             attr_set[ctx->device & 63] = true;
         }
         KZG_CUDA(ctx, cudaMemsetAsync(part_hist, 0, sizeof(uint32_t) * (sg.nparts + 1), ctx->stream));
@@ -1160,7 +1217,8 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums, segoff, cursor,
                heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
     if (use_part_sort)
-        KZG_LAUNCH(ctx, msm_chunk_scatter_kernel, max_chunks, CHUNK_THREADS, 0, mid, pstart, cstart, sg, chunk_hist, cursor, sorted);
+        KZG_LAUNCH(ctx, msm_chunk_scatter_kernel, max_chunks, CHUNK_THREADS, CHUNK_SMEM, mid, pstart, cstart, sg, chunk_hist, cursor,
+                   sorted);
     else
         KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
     timed_end(ctx, KZG_TIMED_MSM_SORT);
