@@ -304,7 +304,7 @@ def run_b200(args):
         "unit": "Tmac/s", "frac": achieved / (imad.value / 1e12) if imad.value else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 points on one GPU, from the ncu --set full
         # capture summarised in profiles/r01_msm_accumulate_full.md (64-byte random gathers cost 128 B each)
-        "traffic": 2.944e10 if (world == 1 and args.log_n == 24) else None,
+        "traffic": 2.769e10 if (world == 1 and args.log_n == 24) else None,   # ncu dram read + write, profiles/r01_msm_accumulate_full.md
         "peak_source": "kzg_bench_imad_peak: IMAD.WIDE.U32 carry chains timed live on this GPU (MEASURED_PEAKS.json has no integer peak)",
         "modmul_peak_tmacs": modmul.value / 1e12,
         "algorithmic_macs_per_launch": macs_per_launch, "executed_macs_per_launch": executed_macs,

@@ -928,17 +928,30 @@ __global__ void msm_horner_kernel(const G1XYZZ* __restrict__ windows, uint32_t n
     store_xyzz(result, acc);
 }
 
-// sum `count` XYZZ points and write the canonical affine encoding
-__global__ void g1_finish_kernel(const G1XYZZ* __restrict__ parts, uint32_t count, G1Affine* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    G1XYZZ acc = xyzz_inf();
-    for (uint32_t i = 0; i < count; i++) {
-        G1XYZZ o = load_xyzz(parts + i);
-        xyzz_add(acc, o);
+// sum `count` XYZZ points and write the canonical affine encoding.  One warp: the partial points (the shards of a
+// multi-GPU MSM, the pieces of a host-scalar MSM) are summed in quad-lane arithmetic -- 8 quads stride over them, then a
+// 3-level butterfly -- and lane 0 does the one inversion.
+__global__ void __launch_bounds__(32) g1_finish_kernel(const G1XYZZ* __restrict__ parts, uint32_t count, G1Affine* __restrict__ out) {
+    if (blockIdx.x != 0) return;
+    const uint32_t lane = threadIdx.x & 31, j = lane & 3;
+    G1XYZZ acc;
+    if (count == 1) {
+        acc = load_xyzz(parts);
+    } else {
+        const uint32_t qm = quad_mask();
+        Fq a = fp_zero<FqP>();
+#pragma unroll 1
+        for (uint32_t k = lane >> 2; k < count; k += 8) {
+            const Fq o = quad_load(parts + k, j);
+            quad_add(a, o, j, qm);
+        }
+        quad_butterfly(a, 16, j, qm);
+        acc = quad_gather(qm, a);
     }
-    G1Affine a = xyzz_to_affine(acc);
-    fp_store(&out->x, a.x);
-    fp_store(&out->y, a.y);
+    if (lane != 0) return;
+    G1Affine r = xyzz_to_affine(acc);
+    fp_store(&out->x, r.x);
+    fp_store(&out->y, r.y);
 }
 
 // ---------------------------------------------------------------------------------------------
