@@ -33,6 +33,9 @@ struct kzg_prover {
     kzg::Fr *ev_acc = nullptr, *co_acc = nullptr;  // S or Z
     kzg::Fr* co_q = nullptr;                        // m coefficients
     kzg::Fr* inv_nx = nullptr;                      // 1 / (n (x_i - 1)) on the coset
+    kzg::Fr* cos = nullptr;                         // columns evaluated on the coset g H_m (queued in round 2, used in round 3)
+    cudaEvent_t cos_ready = nullptr;
+    bool cos_queued = false;
     kzg::Fr beta, gamma, alpha, xi, v;
     std::vector<kzg::Fr> evals;  // round-4 outputs in proof order
     std::vector<void*> owned;
@@ -199,7 +202,10 @@ int kzg_prover_take_evals(kzg_prover* p, uint32_t column, int which, kzg_buf** o
 
 int kzg_prover_destroy(kzg_prover* p) {
     if (!p) return KZG_OK;
+    if (p->cos_queued) cudaStreamWaitEvent(p->ctx->stream, p->cos_ready, 0);  // lane 1 may still be writing p->cos
+    if (p->cos) cudaFreeAsync(p->cos, p->ctx->stream);
     for (void* d : p->owned) cudaFreeAsync(d, p->ctx->stream);
+    if (p->cos_ready) cudaEventDestroy(p->cos_ready);
     delete p;
     return KZG_OK;
 }
@@ -295,6 +301,35 @@ int kzg_prover_create(kzg_ctx* ctx, kzg_srs* srs, int kind, uint32_t n_bits, uin
 }
 
 // ---- round 1 -----------------------------------------------------------------------------------------
+// Round 3 evaluates the columns F, T, S/Z (and the selectors) on the coset g H_m.  None of that needs the challenge
+// alpha, so it is queued on lane 1 (auxiliary stream) as soon as S/Z exists and runs under the commitment of S/Z on
+// lane 0, whose sort and bucket-reduction phases leave the integer pipe idle.
+static int coset_prefetch(kzg_prover* p) {
+    kzg_ctx* ctx = p->ctx;
+    const uint64_t n = p->n, m = p->m;
+    const uint32_t log_m = log2u(m);
+    const uint32_t ncol = p->selected ? 5 : 3;
+    if (!p->cos) KZG_CUDA(ctx, cudaMallocAsync((void**)&p->cos, sizeof(Fr) * m * ncol, ctx->stream));
+    if (!p->cos_ready) KZG_CUDA(ctx, cudaEventCreateWithFlags(&p->cos_ready, cudaEventDisableTiming));
+    const Fr* srcs[5] = {p->co_fc, p->co_tc, p->co_acc, p->co_self, p->co_selt};
+    cudaStream_t main_stream = ctx->stream;
+    KZG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));  // the coefficients and p->cos exist from here on
+    KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    ctx->lane = 1;
+    ctx->stream = ctx->aux_stream;
+    int r = KZG_OK;
+    for (uint32_t c = 0; c < ncol && r == KZG_OK; c++) {
+        Fr* dst = p->cos + (uint64_t)c * m;
+        r = fr_scale_powers(ctx, srcs[c], dst, n, log_m + 1, false, nullptr);  // coef_j * g^j
+        if (r == KZG_OK) r = ntt_run(ctx, dst, n, dst, log_m, false);
+    }
+    cudaEventRecord(p->cos_ready, ctx->aux_stream);
+    ctx->lane = 0;
+    ctx->stream = main_stream;
+    p->cos_queued = true;
+    return r;
+}
+
 int kzg_prover_round1(kzg_prover* p, const uint8_t* const* evals_f_std, const uint8_t* const* evals_t_std,
                       const uint8_t* sel_f, const uint8_t* sel_t, uint8_t* commitments_out) {
     if (!p || !evals_f_std || !evals_t_std || !commitments_out) return KZG_ERR_ARG;
@@ -302,7 +337,8 @@ int kzg_prover_round1(kzg_prover* p, const uint8_t* const* evals_f_std, const ui
     if (p->selected && (!sel_f || !sel_t)) return set_err(ctx, KZG_ERR_ARG, "selected prover needs both selector columns");
     const uint64_t n = p->n;
     const size_t bytes = sizeof(Fr) * n;
-    // all uploads first (they queue on the copy engine), then the arithmetic
+    // all uploads first (they queue on the copy engine), then the arithmetic.  (Splitting the F and T sides over the
+    // two lanes was measured and dropped: concurrent uploads only share the PCIe link, both sides start later.)
     for (uint32_t i = 0; i < p->k; i++) {
         KZG_CUDA(ctx, cudaMemcpyAsync(p->ev_f[i], evals_f_std[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
         KZG_CUDA(ctx, cudaMemcpyAsync(p->ev_t[i], evals_t_std[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -365,6 +401,7 @@ int kzg_prover_round2(kzg_prover* p, const uint8_t beta[32], const uint8_t gamma
                        p->kind == KZG_GRANDSUM ? "The grand-sum polynomial S is not well calculated"
                                                : "The grand-product polynomial Z is not well calculated");
     KZG_TRY(ntt_run(ctx, p->ev_acc, n, p->co_acc, p->n_bits, true));
+    KZG_TRY(coset_prefetch(p));
     KZG_TRY(commit_dev(p, p->co_acc, n, out_acc));
     p->round = 2;
     return KZG_OK;
@@ -402,17 +439,11 @@ int kzg_prover_round3(kzg_prover* p, const uint8_t alpha[32], uint8_t out_q[64])
     KZG_CHECK_LAUNCH(ctx);
     KZG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 256, bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
 
-    // (2) evaluate the columns on the coset g H_m
-    const uint32_t ncol = p->selected ? 5 : 3;
-    Fr* cos = nullptr;
-    KZG_CUDA(ctx, cudaMallocAsync((void**)&cos, sizeof(Fr) * m * ncol, ctx->stream));
-    const Fr* srcs[5] = {p->co_fc, p->co_tc, p->co_acc, p->co_self, p->co_selt};
+    // (2) the columns on the coset g H_m: queued on lane 1 in round 2 (coset_prefetch)
+    if (!p->cos_queued) return set_err(ctx, KZG_ERR_ARG, "prover rounds must run in order");
+    KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->cos_ready, 0));
+    Fr* cos = p->cos;
     int r = KZG_OK;
-    for (uint32_t c = 0; c < ncol && r == KZG_OK; c++) {
-        Fr* dst = cos + (uint64_t)c * m;
-        r = fr_scale_powers(ctx, srcs[c], dst, n, log_m + 1, false, nullptr);  // coef_j * g^j
-        if (r == KZG_OK) r = ntt_run(ctx, dst, n, dst, log_m, false);
-    }
     // (3) pointwise quotient, back to coefficients, undo the coset shift
     if (r == KZG_OK) {
         a.f = cos;
@@ -439,7 +470,9 @@ int kzg_prover_round3(kzg_prover* p, const uint8_t alpha[32], uint8_t out_q[64])
     }
     if (r == KZG_OK) r = ntt_run(ctx, p->co_q, m, p->co_q, log_m, true);
     if (r == KZG_OK) r = fr_scale_powers(ctx, p->co_q, p->co_q, m, log_m + 1, true, nullptr);
-    cudaFreeAsync(cos, ctx->stream);
+    cudaFreeAsync(p->cos, ctx->stream);  // (the main stream has waited for lane 1's last write)
+    p->cos = nullptr;
+    p->cos_queued = false;
     KZG_TRY(r);
     KZG_TRY(commit_dev(p, p->co_q, m, out_q));  // synchronises the stream
     unsigned int flag;

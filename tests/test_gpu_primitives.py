@@ -457,3 +457,26 @@ def test_msm_partition_sort(curve, tau, flavour, c, monkeypatch):
         monkeypatch.delenv("KZGB200_PART_SORT", raising=False)
         curve.check(curve.lib.kzg_msm_set_window(curve.ctx, 0))
         curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+@pytest.mark.parametrize("part_sort", ["0", "1"])
+def test_msm_huge_buckets(curve, tau, part_sort, monkeypatch):
+    """buckets with hundreds of partial sums (one scalar value repeated: the block-tier collapse) next to buckets with a
+    few dozen (warp tier) and ordinary ones, through both sort schemes"""
+    from kzg_grandsums_study_b200._lib import as_ptr
+    n = 9000
+    srs = C.c_void_p()
+    curve.check(curve.lib.kzg_srs_generate(curve.ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
+    try:
+        curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, 12))
+        monkeypatch.setenv("KZGB200_PART_SORT", part_sort)
+        rnd = inputs.random_column(77, n)
+        scalars = [3 if i < 6000 else (5 << 12) if i < 6600 else rnd[i] for i in range(n)]
+        expect = sum(s * pow(tau, i, R) for i, s in enumerate(scalars)) % R
+        buf = curve.to_device(bn.fr_vec_to_std_bytes(scalars))
+        out = bytearray(64)
+        curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out)))
+        assert bytes(out) == bn.g1_to_bytes(bn.g1_mul_gen(expect))
+    finally:
+        monkeypatch.delenv("KZGB200_PART_SORT", raising=False)
+        curve.lib.kzg_srs_free(curve.ctx, srs)
