@@ -31,6 +31,7 @@ TAU_SEED = 1001
 SCALAR_SEED = 6
 PROVE_SEED = 4           # config C4
 MACS_PER_POINT_WINDOW = 10 * 136   # XYZZ mixed add = 8M + 2S = 10 modmul x 136 limb-MACs
+NCU_TRAFFIC_2_24 = None               # DRAM bytes (read + write) of one bucket accumulation at 2^24 points, from ncu (profiles/)
 
 
 def parse_args():
@@ -260,7 +261,10 @@ def run_b200(args):
     launches = curve.launch_count() - launches0
     acc_ms = C.c_double()
     acc_launches = C.c_uint64()
-    curve.check(lib.kzg_ctx_kernel_time(ctx, 0, -1, C.byref(acc_ms), C.byref(acc_launches)))
+    aff_ms = C.c_double()
+    aff_phases = C.c_uint64()
+    curve.check(lib.kzg_ctx_kernel_time(ctx, 5, 0, C.byref(aff_ms), C.byref(aff_phases)))      # batched-affine rounds
+    curve.check(lib.kzg_ctx_kernel_time(ctx, 0, -1, C.byref(acc_ms), C.byref(acc_launches)))   # XYZZ walk; stop timing
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = N / (ms_per_step * 1e-3) / 1e6
@@ -292,26 +296,39 @@ def run_b200(args):
     curve.check(lib.kzg_bench_imad_peak(ctx, 200, C.byref(imad)))
     curve.check(lib.kzg_bench_modmul_peak(ctx, 200, C.byref(modmul)))
     geom = msm_geometry(lib, ctx, srs, shard)
-    acc_ms_per_launch = acc_ms.value / max(1, acc_launches.value)
-    # ALGORITHMIC work: 21 760 limb-MACs per point = 16 windows x one XYZZ mixed add (10 modmul x 136);
-    # the kernel actually executes shard * geom["windows"] mixed adds (fewer with the SRS table's wider windows)
+    # The dominant work is the BUCKET ACCUMULATION: (from ~2^22 points per GPU) `affine_rounds` batched-affine rounds
+    # (msm_aff_forward / fq_batch_inverse / msm_aff_backward, tag 5) that halve the sorted list each time, then the
+    # XYZZ walk msm_accumulate_kernel (tag 0) over what is left.  One "launch" below = one accumulation = one MSM.
+    phase_ms = (acc_ms.value + aff_ms.value) / max(1, acc_launches.value)
+    walk_ms = acc_ms.value / max(1, acc_launches.value)
+    # ALGORITHMIC work: 21 760 limb-MACs per point = 16 windows x one XYZZ mixed add (10 modmul x 136).
+    # EXECUTED: shard * windows entries; an entry absorbed by an affine round costs ~6.3 modmul (3 for its share of the
+    # batch inversion incl. the 4.3 / 16 of the recursive levels, 3 for the chord formulas), one left to the walk 10.
     macs_per_launch = float(shard) * 16 * MACS_PER_POINT_WINDOW
-    executed_macs = float(shard) * geom["windows"] * MACS_PER_POINT_WINDOW
-    achieved = macs_per_launch / (acc_ms_per_launch * 1e-3) / 1e12 if acc_ms_per_launch > 0 else 0.0
+    entries = float(shard) * geom["windows"]
+    left = entries / (1 << geom["affine_rounds"])
+    executed_macs = (left * 10 + (entries - left) * 6.3) * 136
+    achieved = macs_per_launch / (phase_ms * 1e-3) / 1e12 if phase_ms > 0 else 0.0
     peaks, peak_kind = measured_peaks()
+    affine = geom["affine_rounds"] > 0
     roofline = {
-        "bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": imad.value / 1e12,
+        "bound": "imad",
+        "kernel": ("bucket accumulation = %d batched-affine rounds (msm_aff_forward_kernel, batch_*_kernel<FqP>, "
+                   "msm_aff_backward_kernel) + msm_accumulate_kernel" % geom["affine_rounds"]) if affine else "msm_accumulate_kernel",
+        "achieved": achieved, "peak": imad.value / 1e12,
         "unit": "Tmac/s", "frac": achieved / (imad.value / 1e12) if imad.value else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 points on one GPU, from the ncu --set full
-        # capture summarised in profiles/r01_msm_accumulate_full.md (64-byte random gathers cost 128 B each)
-        "traffic": 2.769e10 if (world == 1 and args.log_n == 24) else None,   # ncu dram read + write, profiles/r01_msm_accumulate_full.md
+        # dram__bytes_read.sum + dram__bytes_write.sum of these kernels at 2^24 points on one GPU, summed over one
+        # accumulation, from the ncu capture summarised in profiles/r01_msm_affine.md (64-byte random gathers cost 128 B)
+        "traffic": NCU_TRAFFIC_2_24 if (world == 1 and args.log_n == 24 and geom["affine_rounds"] == 4) else None,
         "peak_source": "kzg_bench_imad_peak: IMAD.WIDE.U32 carry chains timed live on this GPU (MEASURED_PEAKS.json has no integer peak)",
         "modmul_peak_tmacs": modmul.value / 1e12,
         "algorithmic_macs_per_launch": macs_per_launch, "executed_macs_per_launch": executed_macs,
-        "executed_frac": (executed_macs / (acc_ms_per_launch * 1e-3) / imad.value) if acc_ms_per_launch > 0 and imad.value else None,
-        "kernel_ms_per_launch": acc_ms_per_launch,
-        "kernel_share_of_step": acc_ms_per_launch / ms_per_step if ms_per_step else None,
-        "windows": geom["windows"], "window_bits": geom["c"],
+        "executed_frac": (executed_macs / (phase_ms * 1e-3) / imad.value) if phase_ms > 0 and imad.value else None,
+        "kernel_ms_per_launch": phase_ms,
+        "affine_rounds_ms_per_launch": aff_ms.value / max(1, acc_launches.value),
+        "xyzz_walk_ms_per_launch": walk_ms,
+        "kernel_share_of_step": phase_ms / ms_per_step if ms_per_step else None,
+        "windows": geom["windows"], "window_bits": geom["c"], "affine_rounds": geom["affine_rounds"],
         "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_kind": peak_kind,
     }
 
@@ -374,8 +391,9 @@ def run_b200(args):
 def msm_geometry(lib, ctx, srs, n):
     c = C.c_uint32()
     w = C.c_uint32()
-    lib.kzg_msm_geometry(ctx, srs, n, 0, C.byref(c), C.byref(w))
-    return {"c": c.value, "windows": w.value}
+    r = C.c_uint32()
+    lib.kzg_msm_plan(ctx, srs, n, 0, C.byref(c), C.byref(w), C.byref(r))
+    return {"c": c.value, "windows": w.value, "affine_rounds": r.value}
 
 
 def shard_known_scalar(curve, scal_dev, tau, first):

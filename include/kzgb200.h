@@ -61,7 +61,8 @@ int kzg_bench_imad_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second);
  * ceiling once the carry handling (IADD3) and the quotient-digit IMADs of a modular product are included */
 int kzg_bench_modmul_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second);
 /* device time in milliseconds the context's kernels tagged `which` took since the last reset (CUDA events
- * on the context's stream; 0 = msm bucket accumulation).  Used by bench.py for the live roofline figure. */
+ * on the context's stream; 0 = msm bucket accumulation (XYZZ walk), 5 = its batched-affine rounds, 2/3/4 = msm sort /
+ * bucket reduction / finish, 1 = NTT).  Used by bench.py for the live roofline figure. */
 int kzg_ctx_kernel_time(kzg_ctx* ctx, uint32_t which, int reset, double* ms_out, uint64_t* launches_out);
 
 /* ---- SRS ---------------------------------------------------------------------------------------------- */
@@ -158,6 +159,10 @@ int kzg_srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t window_bits);
  * the SRS entry points ignore their table.  kzg_msm_geometry reports what an n-point MSM will use (srs may be
  * NULL for the raw kzg_g1_msm_affine path; montgomery = 1 for kzg_commit's scalars, 0 for standard form). */
 int kzg_msm_geometry(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows);
+/* the same plus the number of batched-affine rounds the bucket accumulation will run before its XYZZ walk (0 below
+ * ~2^22 points; each round adds the entries of every bucket pairwise with a shared inversion) */
+int kzg_msm_plan(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows,
+                 uint32_t* affine_rounds);
 int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c);
 
 /* ---- fused provers (prover.js:144-413 and the grand-product twin) --------------------------------------- */

@@ -74,6 +74,7 @@ SIGNATURES = {
     "kzg_srs_msm_host": (i32, [vp, vp, u64, vp, u64, vp]),
     "kzg_srs_precompute": (i32, [vp, vp, u32]),
     "kzg_msm_geometry": (i32, [vp, vp, u64, i32, C.POINTER(u32), C.POINTER(u32)]),
+    "kzg_msm_plan": (i32, [vp, vp, u64, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
     "kzg_msm_set_window": (i32, [vp, u32]),
     "kzg_prover_create": (i32, [vp, vp, i32, u32, u32, i32, C.POINTER(vp)]),
     "kzg_prover_destroy": (i32, [vp]),

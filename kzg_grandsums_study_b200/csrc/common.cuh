@@ -19,7 +19,7 @@ struct kzg_ctx {
     uint32_t msm_window = 0;  // 0 = auto
     // optional per-kernel device timing (bench.py's live roofline): event pairs around tagged launches
     bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[5];
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[6];
     std::vector<cudaEvent_t> event_pool;
     // twiddle tables (device): W = w_{2^26}; lo[i] = W^i, hi[j] = W^(j * 8192); [0] forward, [1] inverse
     kzg::Fr* tw_lo[2] = {nullptr, nullptr};
@@ -99,7 +99,7 @@ int set_err(kzg_ctx* ctx, int code, const std::string& msg);
 
 // tags for kzg_ctx_kernel_time
 enum { KZG_TIMED_MSM_ACCUMULATE = 0, KZG_TIMED_NTT = 1, KZG_TIMED_MSM_SORT = 2, KZG_TIMED_MSM_REDUCE = 3,
-       KZG_TIMED_MSM_FINISH = 4, KZG_TIMED_TAGS = 5 };
+       KZG_TIMED_MSM_FINISH = 4, KZG_TIMED_MSM_AFFINE = 5, KZG_TIMED_TAGS = 6 };
 void timed_begin(kzg_ctx* ctx, int tag);
 void timed_end(kzg_ctx* ctx, int tag);
 
@@ -136,6 +136,7 @@ int msm_run_batch(kzg_ctx* ctx, const MsmJob* jobs, uint32_t count, uint8_t* out
 // frops.cu
 int fr_convert(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n, bool to_mont);
 int fr_batch_inverse(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n);
+int fq_batch_inverse(kzg_ctx* ctx, const Fq* in, Fq* out, uint64_t n);  // no zeros expected (0 -> 0 all the same)
 int poly_degree(kzg_ctx* ctx, const Fr* a, uint64_t n, uint64_t* degree);
 int poly_evaluate_multi(kzg_ctx* ctx, const Fr* const* polys, const uint64_t* lens, const Fr* points, uint32_t count,
                         Fr* out_host);

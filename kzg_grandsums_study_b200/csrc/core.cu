@@ -241,6 +241,13 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
         return KZG_ERR_CUDA;
     }
     ctx->no_split = getenv("KZGB200_NO_SPLIT") != nullptr;
+    if (const char* ov = getenv("KZGB200_L2_FETCH")) {  // experiment: bytes the L2 fetches from DRAM per miss
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(ov));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[kzgb200] L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(le));
+    }
     ctx->pinned_bytes = 1 << 16;
     ctx->dev_small_bytes = 1 << 16;
     if (cudaMallocHost((void**)&ctx->pinned, ctx->pinned_bytes) != cudaSuccess ||

@@ -100,20 +100,23 @@ int poly_linear_combination(kzg_ctx* ctx, Fr* out, uint64_t n_out, const Fr* con
 // ------------------------------------------------------------------------------------------------
 // warp helpers over Fr
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Fr shfl_up_fr(const Fr& v, uint32_t d) {
-    Fr r;
+template <class P>
+__device__ __forceinline__ Fp<P> shfl_up_fr(const Fp<P>& v, uint32_t d) {
+    Fp<P> r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.l[i] = __shfl_up_sync(0xffffffffu, v.l[i], d);
     return r;
 }
-__device__ __forceinline__ Fr shfl_down_fr(const Fr& v, uint32_t d) {
-    Fr r;
+template <class P>
+__device__ __forceinline__ Fp<P> shfl_down_fr(const Fp<P>& v, uint32_t d) {
+    Fp<P> r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], d);
     return r;
 }
-__device__ __forceinline__ Fr shfl_fr(const Fr& v, uint32_t src) {
-    Fr r;
+template <class P>
+__device__ __forceinline__ Fp<P> shfl_fr(const Fp<P>& v, uint32_t src) {
+    Fp<P> r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
     return r;
@@ -125,53 +128,54 @@ __device__ __forceinline__ Fr shfl_fr(const Fr& v, uint32_t src) {
 // Larger inputs go through the two-level scheme below (fr_batch_inverse).
 // ------------------------------------------------------------------------------------------------
 constexpr int BI_E = 8;
-__global__ void __launch_bounds__(EW_THREADS) batch_inverse_kernel(const Fr* __restrict__ in, Fr* __restrict__ out,
+template <class P>
+__global__ void __launch_bounds__(EW_THREADS) batch_inverse_kernel(const Fp<P>* __restrict__ in, Fp<P>* __restrict__ out,
                                                                    uint64_t n) {
     const uint64_t base = (uint64_t)blockIdx.x * (EW_THREADS * BI_E) + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
-    Fr v[BI_E], p[BI_E];
+    Fp<P> v[BI_E], p[BI_E];
     uint32_t zmask = 0;
-    const Fr one = fp_one<FrP>();
+    const Fp<P> one = fp_one<P>();
 #pragma unroll
     for (int k = 0; k < BI_E; k++) {
         uint64_t i = base + (uint64_t)k * EW_THREADS;
-        v[k] = i < n ? fp_load<FrP>(in + i) : one;
+        v[k] = i < n ? fp_load<P>(in + i) : one;
         if (fp_is_zero(v[k])) {
             zmask |= 1u << k;
             v[k] = one;
         }
         p[k] = k == 0 ? v[0] : fp_mul(p[k - 1], v[k]);
     }
-    const Fr total = p[BI_E - 1];
+    const Fp<P> total = p[BI_E - 1];
     // inclusive prefix products over lanes
-    Fr pre = total;
+    Fp<P> pre = total;
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1) {
-        Fr o = shfl_up_fr(pre, d);
+        Fp<P> o = shfl_up_fr(pre, d);
         if (lane >= d) pre = fp_mul(pre, o);
     }
     // inclusive suffix products over lanes
-    Fr suf = total;
+    Fp<P> suf = total;
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1) {
-        Fr o = shfl_down_fr(suf, d);
+        Fp<P> o = shfl_down_fr(suf, d);
         if (lane + d < 32) suf = fp_mul(suf, o);
     }
-    Fr inv_all = pre;  // lane 31 holds the warp product
+    Fp<P> inv_all = pre;  // lane 31 holds the warp product
     if (lane == 31) inv_all = fp_inv(pre);
     inv_all = shfl_fr(inv_all, 31);
     // 1 / total_lane = prefix_{lane-1} * suffix_{lane+1} * inv_all
-    Fr pre_ex = shfl_up_fr(pre, 1);
-    Fr suf_ex = shfl_down_fr(suf, 1);
-    Fr inv_t = inv_all;
+    Fp<P> pre_ex = shfl_up_fr(pre, 1);
+    Fp<P> suf_ex = shfl_down_fr(suf, 1);
+    Fp<P> inv_t = inv_all;
     if (lane > 0) inv_t = fp_mul(inv_t, pre_ex);
     if (lane < 31) inv_t = fp_mul(inv_t, suf_ex);
 #pragma unroll
     for (int k = BI_E - 1; k >= 0; k--) {
-        Fr r = k == 0 ? inv_t : fp_mul(inv_t, p[k - 1]);
+        Fp<P> r = k == 0 ? inv_t : fp_mul(inv_t, p[k - 1]);
         if (k > 0) inv_t = fp_mul(inv_t, v[k]);
         uint64_t i = base + (uint64_t)k * EW_THREADS;
-        if (i < n) fp_store(out + i, (zmask >> k) & 1 ? fp_zero<FrP>() : r);
+        if (i < n) fp_store(out + i, (zmask >> k) & 1 ? fp_zero<P>() : r);
     }
 }
 // Large inputs: two-level Montgomery trick across kernels, so that the number of Fermat inversions (254
@@ -180,67 +184,73 @@ __global__ void __launch_bounds__(EW_THREADS) batch_inverse_kernel(const Fr* __r
 //   (recurse): P <- 1 / P   (an input 8 times smaller)
 //   apply    : thread g re-reads its elements, rebuilds its prefix products and peels the inverses off P[g]
 // ~4.3 modmul and 96 bytes per element.  Element k of thread (block, t) is base + k * blockDim + t (coalesced).
-__global__ void __launch_bounds__(EW_THREADS) batch_products_kernel(const Fr* __restrict__ in, Fr* __restrict__ prod, uint64_t n) {
+template <class P>
+__global__ void __launch_bounds__(EW_THREADS) batch_products_kernel(const Fp<P>* __restrict__ in, Fp<P>* __restrict__ prod, uint64_t n) {
     const uint64_t base = (uint64_t)blockIdx.x * (EW_THREADS * BI_E) + threadIdx.x;
-    Fr p = fp_one<FrP>();
+    Fp<P> p = fp_one<P>();
 #pragma unroll
     for (int k = 0; k < BI_E; k++) {
         uint64_t i = base + (uint64_t)k * EW_THREADS;
         if (i < n) {
-            Fr v = fp_load<FrP>(in + i);
+            Fp<P> v = fp_load<P>(in + i);
             if (!fp_is_zero(v)) p = fp_mul(p, v);
         }
     }
     fp_store(prod + (uint64_t)blockIdx.x * EW_THREADS + threadIdx.x, p);
 }
 
-__global__ void __launch_bounds__(EW_THREADS) batch_apply_kernel(const Fr* __restrict__ in, const Fr* __restrict__ prod_inv,
-                                                                 Fr* __restrict__ out, uint64_t n) {
+template <class P>
+__global__ void __launch_bounds__(EW_THREADS) batch_apply_kernel(const Fp<P>* __restrict__ in, const Fp<P>* __restrict__ prod_inv,
+                                                                 Fp<P>* __restrict__ out, uint64_t n) {
     const uint64_t base = (uint64_t)blockIdx.x * (EW_THREADS * BI_E) + threadIdx.x;
-    Fr v[BI_E], p[BI_E];
+    Fp<P> v[BI_E], p[BI_E];
     uint32_t zmask = 0;
-    const Fr one = fp_one<FrP>();
+    const Fp<P> one = fp_one<P>();
 #pragma unroll
     for (int k = 0; k < BI_E; k++) {
         uint64_t i = base + (uint64_t)k * EW_THREADS;
-        v[k] = i < n ? fp_load<FrP>(in + i) : one;
+        v[k] = i < n ? fp_load<P>(in + i) : one;
         if (fp_is_zero(v[k])) {
             zmask |= 1u << k;
             v[k] = one;
         }
         p[k] = k == 0 ? v[0] : fp_mul(p[k - 1], v[k]);
     }
-    Fr inv_t = fp_load<FrP>(prod_inv + (uint64_t)blockIdx.x * EW_THREADS + threadIdx.x);
+    Fp<P> inv_t = fp_load<P>(prod_inv + (uint64_t)blockIdx.x * EW_THREADS + threadIdx.x);
 #pragma unroll
     for (int k = BI_E - 1; k >= 0; k--) {
-        Fr r = k == 0 ? inv_t : fp_mul(inv_t, p[k - 1]);
+        Fp<P> r = k == 0 ? inv_t : fp_mul(inv_t, p[k - 1]);
         if (k > 0) inv_t = fp_mul(inv_t, v[k]);
         uint64_t i = base + (uint64_t)k * EW_THREADS;
-        if (i < n) fp_store(out + i, (zmask >> k) & 1 ? fp_zero<FrP>() : r);
+        if (i < n) fp_store(out + i, (zmask >> k) & 1 ? fp_zero<P>() : r);
     }
 }
 
-int fr_batch_inverse(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n) {
+template <class P>
+static int fp_batch_inverse(kzg_ctx* ctx, const Fp<P>* in, Fp<P>* out, uint64_t n) {
     if (n == 0) return KZG_OK;
     const uint32_t blocks = grid_for(n, EW_THREADS * BI_E);
     if (n <= 4096) {
-        KZG_LAUNCH(ctx, batch_inverse_kernel, blocks, EW_THREADS, 0, in, out, n);
+        KZG_LAUNCH(ctx, batch_inverse_kernel<P>, blocks, EW_THREADS, 0, in, out, n);
         KZG_CHECK_LAUNCH(ctx);
         return KZG_OK;
     }
     const uint64_t m = (uint64_t)blocks * EW_THREADS;  // thread products (never zero)
-    Fr* prod = nullptr;
-    KZG_CUDA(ctx, cudaMallocAsync((void**)&prod, sizeof(Fr) * m, ctx->stream));
-    KZG_LAUNCH(ctx, batch_products_kernel, blocks, EW_THREADS, 0, in, prod, n);
-    int r = fr_batch_inverse(ctx, prod, prod, m);
+    Fp<P>* prod = nullptr;
+    KZG_CUDA(ctx, cudaMallocAsync((void**)&prod, sizeof(Fp<P>) * m, ctx->stream));
+    KZG_LAUNCH(ctx, batch_products_kernel<P>, blocks, EW_THREADS, 0, in, prod, n);
+    int r = fp_batch_inverse<P>(ctx, prod, prod, m);
     if (r == KZG_OK) {
-        KZG_LAUNCH(ctx, batch_apply_kernel, blocks, EW_THREADS, 0, in, prod, out, n);
+        KZG_LAUNCH(ctx, batch_apply_kernel<P>, blocks, EW_THREADS, 0, in, prod, out, n);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, cudaGetErrorString(e));
     }
     cudaFreeAsync(prod, ctx->stream);
     return r;
 }
+int fr_batch_inverse(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n) { return fp_batch_inverse<FrP>(ctx, in, out, n); }
+// the same over the base field: the batched-affine bucket rounds of the MSM (msm.cu)
+int fq_batch_inverse(kzg_ctx* ctx, const Fq* in, Fq* out, uint64_t n) { return fp_batch_inverse<FqP>(ctx, in, out, n); }
 
 // ------------------------------------------------------------------------------------------------
 // grand-sum / grand-product terms.  kind 0: num = t'*selF - f'*selT, den = f'*t'  (f' = F+gamma ...)

@@ -142,9 +142,11 @@ constexpr uint32_t HUGE_PARTS = 256;
 __device__ __forceinline__ uint32_t parts_of(uint32_t off, uint32_t cnt, uint32_t slice) {
     return cnt == 0 ? 0u : (off + cnt - 1) / slice - off / slice + 1;
 }
+// `shift` batched-affine rounds (below) leave ceil(count / 2^shift) points in a bucket
 __device__ __forceinline__ uint32_t scan_input(int mode, const uint32_t* __restrict__ counts,
-                                               const uint32_t* __restrict__ offsets, uint32_t k, uint32_t slice) {
-    uint32_t cnt = counts[k];
+                                               const uint32_t* __restrict__ offsets, uint32_t k, uint32_t slice,
+                                               uint32_t shift) {
+    uint32_t cnt = (counts[k] + ((1u << shift) - 1u)) >> shift;
     return mode == 0 ? cnt : parts_of(offsets[k], cnt, slice);
 }
 
@@ -172,14 +174,15 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t* sh, uin
 
 __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_tiles_kernel(int mode, const uint32_t* __restrict__ counts,
                                                                       const uint32_t* __restrict__ offsets, uint32_t nkeys,
-                                                                      uint32_t slice, uint32_t* __restrict__ tile_sums) {
+                                                                      uint32_t slice, uint32_t shift,
+                                                                      uint32_t* __restrict__ tile_sums) {
     __shared__ uint32_t sh[SCAN_THREADS / 32];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x;
     uint32_t acc = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         uint32_t i = base + k * SCAN_THREADS;
-        if (i < nkeys) acc += scan_input(mode, counts, offsets, i, slice);
+        if (i < nkeys) acc += scan_input(mode, counts, offsets, i, slice, shift);
     }
     uint32_t tot;
     block_scan_u32(acc, sh, tot);
@@ -209,7 +212,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_sums_kernel(uint32_t* _
 
 __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, const uint32_t* __restrict__ counts,
                                                                       const uint32_t* __restrict__ offsets, uint32_t nkeys,
-                                                                      uint32_t slice, const uint32_t* __restrict__ tile_sums,
+                                                                      uint32_t slice, uint32_t shift,
+                                                                      const uint32_t* __restrict__ tile_sums,
                                                                       uint32_t* __restrict__ out, uint32_t* __restrict__ cursor,
                                                                       uint32_t* __restrict__ heavy,
                                                                       uint32_t* __restrict__ heavy_count,
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, 
 #pragma unroll
     for (int k = 0; k < SCAN_PER_THREAD; k++) {
         uint32_t i = base + k;
-        val[k] = i < nkeys ? scan_input(mode, counts, offsets, i, slice) : 0;
+        val[k] = i < nkeys ? scan_input(mode, counts, offsets, i, slice, shift) : 0;
         acc += val[k];
         nmulti += (val[k] >= 2 && val[k] <= HEAVY_PARTS) ? 1u : 0u;
     }
@@ -592,6 +596,8 @@ __device__ __forceinline__ G1XYZZ load_xyzz(const G1XYZZ* p) {
 // One thread per slice of `slice` consecutive entries of the sorted list: equal work per lane no matter how
 // the bucket sizes fluctuate.  Whenever the walk crosses a bucket boundary the running sum is parked in the
 // partial-sum slot of (bucket, slice):  pbase[key] + (slice index - first slice of the bucket).
+// DIRECT: the list is a dense array of points in bucket order (what the batched-affine rounds below leave), not indices.
+template <bool DIRECT>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __restrict__ bases,
                                                              const uint32_t* __restrict__ sorted,
                                                              const uint32_t* __restrict__ offsets,
@@ -614,8 +620,8 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
     uint32_t key_end = offsets[key + 1];
 
     G1XYZZ acc = xyzz_inf();
-    uint32_t e = sorted[begin];
-    G1Affine p = load_affine(bases + (e & 0x7fffffffu));
+    uint32_t e = DIRECT ? begin : sorted[begin];
+    G1Affine p = load_affine(bases + (DIRECT ? e : e & 0x7fffffffu));
     for (uint32_t j = begin; j < end; j++) {
         if (j == key_end) {  // bucket boundary inside the slice
             store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
@@ -629,15 +635,272 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
         uint32_t e_next = e;
         G1Affine p_next = p;
         if (j + 1 < end) {
-            e_next = sorted[j + 1];
-            p_next = load_affine(bases + (e_next & 0x7fffffffu));
+            e_next = DIRECT ? j + 1 : sorted[j + 1];
+            p_next = load_affine(bases + (DIRECT ? e_next : e_next & 0x7fffffffu));
         }
-        if (e >> 31) p.y = fp_neg(p.y);
+        if (!DIRECT && (e >> 31)) p.y = fp_neg(p.y);
         xyzz_madd(acc, p);
         e = e_next;
         p = p_next;
     }
     store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched-affine bucket rounds.  The XYZZ walk above pays 10 modmul per entry because it never inverts.  With many
+// independent additions in flight the inversions can be shared (Montgomery's trick), and an AFFINE addition
+//     lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1
+// then costs 3 modmul for its share of the batch inversion + 3 for the formulas = 6.  One round adds the points of
+// every bucket PAIRWISE by position (entries 2i and 2i+1 of the bucket -> point i of the bucket in the next list; an odd
+// last entry is copied), so a round halves the list and all of its additions are independent.  After a few rounds the
+// dense list that is left (ceil(count / 2^rounds) points per bucket, still in bucket order) goes through the XYZZ
+// walk and the bucket reduction as before.  Per round:
+//   msm_aff_forward   thread t owns AFF_M consecutive OUTPUT points: denominators d_j (x only: 32 B per operand),
+//                     exclusive prefix products -> prefix[j][t], thread product -> totals[t]
+//   fq_batch_inverse  totals <- 1 / totals   (frops.cu, ~4.3 / AFF_M modmul per addition)
+//   msm_aff_backward  walks its outputs backwards peeling 1 / d_j off the inverse (2 modmul), finishes the additions,
+//                     writes the 64-byte affine results
+// Exceptional pairs are decided from the operands alone, identically in both kernels: an operand at infinity, P + P
+// (tangent: d = 2 y, numerator 3 x^2), P + (-P) = infinity; they put d = 1 into the batch where no quotient is needed.
+// ---------------------------------------------------------------------------------------------
+constexpr int AFF_M = 16;
+constexpr int AFF_THREADS = 128;
+struct AffRound {
+    const G1Affine* bases;    // round 1: window table / points, addressed through `sorted` (index | sign << 31)
+    const uint32_t* sorted;   // round 1 only, nullptr afterwards
+    const G1Affine* in;       // later rounds: the dense list left by the previous round
+    const uint32_t* off_in;   // bucket offsets of the input list  (nkeys + 1)
+    const uint32_t* off_out;  // bucket offsets of the output list (nkeys + 1): scan of ceil(count / 2)
+    uint32_t nkeys;
+    uint32_t nthreads;        // threads of the round = row stride of prefix[][]
+};
+enum { AFF_ADD = 0, AFF_TAKE_1 = 1, AFF_TAKE_2 = 2, AFF_DOUBLE = 3, AFF_INF = 4 };
+
+__device__ __forceinline__ Fq load_fq_ldg(const Fq* p) {
+    Fq r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+// operand handles: position in the dense input list, or (round 1) the sorted entry itself: index | sign << 31
+template <bool INDEXED>
+__device__ __forceinline__ const G1Affine* aff_operand(const AffRound& a, uint32_t h, uint32_t& neg) {
+    if (INDEXED) {
+        neg = h >> 31;
+        return a.bases + (h & 0x7fffffffu);
+    }
+    neg = 0;
+    return a.in + h;
+}
+template <bool INDEXED>
+__device__ __forceinline__ G1Affine aff_load_point(const AffRound& a, uint32_t h) {
+    uint32_t neg;
+    const G1Affine* q = aff_operand<INDEXED>(a, h, neg);
+    G1Affine p = load_affine(q);
+    if (neg) p.y = fp_neg(p.y);
+    return p;
+}
+// kind of the pair and the denominator it contributes to the batch
+__device__ __forceinline__ int aff_classify(const G1Affine& p1, const G1Affine& p2, Fq& d) {
+    d = fp_one<FqP>();
+    if (g1_affine_is_inf(p1)) return AFF_TAKE_2;
+    if (g1_affine_is_inf(p2)) return AFF_TAKE_1;
+    if (fp_eq(p1.x, p2.x)) {
+        if (fp_eq(p1.y, p2.y) && !fp_is_zero(p1.y)) {
+            d = fp_dbl(p1.y);
+            return AFF_DOUBLE;
+        }
+        return AFF_INF;
+    }
+    d = fp_sub(p2.x, p1.x);
+    return AFF_ADD;
+}
+// Walk over the output points of one thread, one bucket at a time: output o of bucket `key` takes the entries
+// 2 (o - out_begin) and 2 (o - out_begin) + 1 of the bucket's input run (the second one only if it exists: `pair`).
+// The loops below are real loops, not unrolled ones: a body of five inlined Montgomery products is ~17 KB of code, and
+// the unrolled version (8 bodies, every warp running through 150 KB of straight-line code once) was bound by
+// instruction fetch (issue-active 15 %).
+struct AffCursor {
+    uint32_t key, out_begin, out_end, in_begin, in_end;
+};
+__device__ __forceinline__ AffCursor aff_seek(const AffRound& a, uint32_t o) {
+    uint32_t lo = 0, hi = a.nkeys;  // invariant: off_out[lo] <= o < off_out[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.off_out[mid] <= o) lo = mid; else hi = mid;
+    }
+    AffCursor c;
+    c.key = lo;
+    c.out_begin = a.off_out[lo];
+    c.out_end = a.off_out[lo + 1];
+    c.in_begin = a.off_in[lo];
+    c.in_end = a.off_in[lo + 1];
+    return c;
+}
+template <bool INDEXED>
+__device__ __forceinline__ void aff_handles(const AffRound& a, const AffCursor& c, uint32_t o, uint32_t& h1, uint32_t& h2, bool& pair) {
+    const uint32_t i0 = c.in_begin + 2 * (o - c.out_begin);
+    pair = i0 + 1 < c.in_end;
+    h1 = INDEXED ? a.sorted[i0] : i0;
+    h2 = INDEXED ? (pair ? a.sorted[i0 + 1] : 0u) : i0 + 1;
+}
+__device__ __forceinline__ void aff_step_up(const AffRound& a, AffCursor& c, uint32_t o) {  // o = previous output + 1
+    if (o >= c.out_end) {
+        do {
+            c.key++;
+            c.out_end = a.off_out[c.key + 1];
+        } while (c.out_end <= o);
+        c.out_begin = a.off_out[c.key];
+        c.in_begin = a.off_in[c.key];
+        c.in_end = a.off_in[c.key + 1];
+    }
+}
+__device__ __forceinline__ void aff_step_down(const AffRound& a, AffCursor& c, uint32_t o) {  // o = previous output - 1
+    if (o < c.out_begin) {
+        do {
+            c.key--;
+            c.out_begin = a.off_out[c.key];
+        } while (c.out_begin > o);
+        c.out_end = a.off_out[c.key + 1];
+        c.in_begin = a.off_in[c.key];
+        c.in_end = a.off_in[c.key + 1];
+    }
+}
+
+template <bool INDEXED>
+__global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRound a, uint32_t m, Fq* __restrict__ prefix,
+                                                                         Fq* __restrict__ totals) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nthreads) return;
+    Fq acc = fp_one<FqP>();
+    const uint32_t total = a.off_out[a.nkeys];
+    const uint64_t begin64 = (uint64_t)t * m;
+    if (begin64 < total) {
+        const uint32_t begin = (uint32_t)begin64;
+        const uint32_t end = (uint32_t)min((uint64_t)total, begin64 + m);
+        AffCursor c = aff_seek(a, begin);
+        uint32_t h1, h2, neg;
+        bool pair;
+        Fq x1, x2;  // x coordinates of the pair in hand, fetched one iteration ahead
+        aff_handles<INDEXED>(a, c, begin, h1, h2, pair);
+        if (pair) {
+            x1 = load_fq_ldg(&aff_operand<INDEXED>(a, h1, neg)->x);
+            x2 = load_fq_ldg(&aff_operand<INDEXED>(a, h2, neg)->x);
+        }
+        Fq* pre = prefix + t;
+#pragma unroll 1
+        for (uint32_t o = begin; o < end; o++, pre += a.nthreads) {
+            uint32_t nh1 = 0, nh2 = 0;
+            bool npair = false;
+            Fq nx1, nx2;
+            if (o + 1 < end) {
+                aff_step_up(a, c, o + 1);
+                aff_handles<INDEXED>(a, c, o + 1, nh1, nh2, npair);
+                if (npair) {
+                    nx1 = load_fq_ldg(&aff_operand<INDEXED>(a, nh1, neg)->x);
+                    nx2 = load_fq_ldg(&aff_operand<INDEXED>(a, nh2, neg)->x);
+                }
+            }
+            if (pair) {
+                Fq d;
+                if (fp_eq(x1, x2) || fp_is_zero(x1) || fp_is_zero(x2)) {  // exceptional: decide on the full points
+                    const G1Affine p1 = aff_load_point<INDEXED>(a, h1), p2 = aff_load_point<INDEXED>(a, h2);
+                    aff_classify(p1, p2, d);
+                } else {
+                    d = fp_sub(x2, x1);
+                }
+                fp_store(pre, acc);
+                acc = fp_mul(acc, d);
+            }
+            h1 = nh1;
+            h2 = nh2;
+            pair = npair;
+            x1 = nx1;
+            x2 = nx2;
+        }
+    }
+    fp_store(totals + t, acc);
+}
+
+__device__ __forceinline__ void store_affine(G1Affine* p, const G1Affine& v) {
+    fp_store(&p->x, v.x);
+    fp_store(&p->y, v.y);
+}
+
+template <bool INDEXED>
+__global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRound a, uint32_t m, const Fq* __restrict__ prefix,
+                                                                          const Fq* __restrict__ inv_totals,
+                                                                          G1Affine* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nthreads) return;
+    const uint32_t total = a.off_out[a.nkeys];
+    const uint64_t begin64 = (uint64_t)t * m;
+    if (begin64 >= total) return;
+    const uint32_t begin = (uint32_t)begin64;
+    const uint32_t end = (uint32_t)min((uint64_t)total, begin64 + m);
+    Fq s = load_fq_ldg(inv_totals + t);  // 1 / (d_0 ... d_j) while pair j is being finished
+    // Software pipeline, one output deep: the operands and the prefix product of output o - 1 are requested before the
+    // addition of output o is computed.  (Measured on B200 at 2^22 points: a second stage for the handles changed
+    // nothing, a third one with prefetch.global.L2 for the operands made round 1 20 % slower.)
+    AffCursor c = aff_seek(a, end - 1);
+    uint32_t h1, h2;
+    bool pair;
+    G1Affine p1, p2;
+    Fq pre;
+    aff_handles<INDEXED>(a, c, end - 1, h1, h2, pair);
+    const Fq* pre_ptr = prefix + (uint64_t)(end - 1 - begin) * a.nthreads + t;
+    p1 = aff_load_point<INDEXED>(a, h1);
+    if (pair) {
+        p2 = aff_load_point<INDEXED>(a, h2);
+        pre = load_fq_ldg(pre_ptr);
+    }
+#pragma unroll 1
+    for (uint32_t o = end - 1;; o--, pre_ptr -= a.nthreads) {
+        const bool more = o > begin;
+        bool q_pair = false;  // (o - 1)
+        G1Affine n1, n2;
+        Fq npre;
+        if (more) {
+            aff_step_down(a, c, o - 1);
+            aff_handles<INDEXED>(a, c, o - 1, h1, h2, q_pair);
+            n1 = aff_load_point<INDEXED>(a, h1);
+            if (q_pair) {
+                n2 = aff_load_point<INDEXED>(a, h2);
+                npre = load_fq_ldg(pre_ptr - a.nthreads);
+            }
+        }
+        G1Affine r = p1;
+        if (pair) {
+            Fq d;
+            const int kind = aff_classify(r, p2, d);
+            const Fq inv = fp_mul(s, pre);
+            s = fp_mul(s, d);
+            if (kind == AFF_ADD || kind == AFF_DOUBLE) {
+                Fq num = fp_sub(p2.y, r.y);
+                if (kind == AFF_DOUBLE) {
+                    const Fq xx = fp_sqr(r.x);
+                    num = fp_add(fp_dbl(xx), xx);
+                }
+                const Fq lam = fp_mul(num, inv);
+                const Fq x3 = fp_sub(fp_sub(fp_sqr(lam), r.x), p2.x);
+                r.y = fp_sub(fp_mul(lam, fp_sub(r.x, x3)), r.y);
+                r.x = x3;
+            } else if (kind == AFF_TAKE_2) {
+                r = p2;
+            } else if (kind == AFF_INF) {
+                r.x = fp_zero<FqP>();
+                r.y = fp_zero<FqP>();
+            }
+        }
+        store_affine(out + o, r);
+        if (!more) break;
+        p1 = n1;
+        p2 = n2;
+        pre = npre;
+        pair = q_pair;
+    }
 }
 
 // The kernels after the accumulation are latency-bound (few warps, long dependent chains) and run once per MSM, so
@@ -1036,6 +1299,9 @@ static uint32_t auto_window_raw(uint64_t n) {
 //   + 4.6 * 2^(c-1)               bucket reduction (measured: 0.64 ms at 2^19 buckets, 1.96 ms at 2^21, ~0.25 ms of it
 //                                 independent of the bucket count)
 constexpr uint64_t PART_SORT_MIN_ENTRIES = 1ull << 22;
+constexpr uint64_t AFF_MIN_ENTRIES = 48ull << 20;  // from 2^22 points on (13 digits each)
+constexpr uint64_t AFF_MIN_LEFT = 1ull << 23;
+constexpr uint32_t AFF_MAX_ROUNDS = 6;
 uint32_t msm_table_window(uint64_t n) {
     uint32_t best = 4;
     double best_cost = 1e300;
@@ -1086,6 +1352,29 @@ static MsmGeom msm_geometry(kzg_ctx* ctx, const MsmBases& b, uint64_t n, bool mo
     return g;
 }
 
+// batched-affine rounds before the XYZZ walk.  Measured on B200 (profiles/r01_msm_affine.md): a round over DENSE
+// points runs at 0.09 ns per addition against 0.16 ns for the XYZZ walk, but round 1 gathers its operands from the
+// window table twice (x for the denominators, then the points) at 128 B of DRAM traffic per 64-byte point and only
+// breaks even, and every round pays ~0.25 ms of latency-bound launches (scan, the tail of the batch inversion).
+// So: a round only while the list it produces keeps >= 2^23 points and its buckets hold >= 6 entries on average.
+static uint32_t msm_affine_rounds(uint64_t max_entries, uint32_t nkeys) {
+    uint32_t aff_rounds = 0;
+    if (max_entries >= AFF_MIN_ENTRIES) {
+        double fill = (double)max_entries / nkeys;
+        uint64_t left = max_entries / 2;
+        while (aff_rounds < AFF_MAX_ROUNDS && fill >= 6.0 && left >= AFF_MIN_LEFT) {
+            aff_rounds++;
+            fill *= 0.5;
+            left /= 2;
+        }
+    }
+    if (const char* ov = getenv("KZGB200_AFF_ROUNDS")) {  // tuning / A-B tests
+        aff_rounds = (uint32_t)atoi(ov);
+        if (aff_rounds > AFF_MAX_ROUNDS) aff_rounds = AFF_MAX_ROUNDS;
+    }
+    return aff_rounds;
+}
+
 int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev) {
     if (n == 0) {
         KZG_CUDA(ctx, cudaMemsetAsync(result_dev, 0, sizeof(G1XYZZ), ctx->stream));
@@ -1096,15 +1385,27 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const uint32_t nkeys = g.nsets * g.nbuckets;
     const uint64_t max_entries = n * g.nwin;
     if (max_entries >= (1ull << 32)) return set_err(ctx, KZG_ERR_ARG, "msm: n * windows exceeds 2^32 entries");
+    const uint32_t aff_rounds = msm_affine_rounds(max_entries, nkeys);
+    uint32_t aff_m = AFF_M;  // output points per thread of a round
+    if (const char* ov = getenv("KZGB200_AFF_M")) {
+        aff_m = (uint32_t)atoi(ov);
+        if (aff_m < 1) aff_m = 1;
+        if (aff_m > 256) aff_m = 256;
+    }
+    // upper bounds of the list lengths: sum_b ceil(k_b / 2) <= (entries + buckets) / 2
+    uint64_t aff_entries[AFF_MAX_ROUNDS + 1];
+    aff_entries[0] = max_entries;
+    for (uint32_t r = 1; r <= aff_rounds; r++) aff_entries[r] = (aff_entries[r - 1] + nkeys) / 2 + 1;
+    const uint64_t walk_entries = aff_entries[aff_rounds];  // what the XYZZ walk sees
     // slice length: a few average buckets (every slice start costs one extra partial sum), but short enough to
     // give every SM several waves of equal-sized tasks
-    uint64_t slice = 4 * (max_entries / nkeys + 1);
+    uint64_t slice = 4 * (walk_entries / nkeys + 1);
     const uint64_t waves = (uint64_t)ctx->sm_count * 512 * 4;
-    if (slice > max_entries / waves) slice = max_entries / waves;
+    if (slice > walk_entries / waves) slice = walk_entries / waves;
     if (slice < 16) slice = 16;
     if (slice > 512) slice = 512;
     g.seg = (uint32_t)slice;
-    const uint64_t max_tasks = (max_entries + slice - 1) / slice;
+    const uint64_t max_tasks = (walk_entries + slice - 1) / slice;
     const uint64_t max_parts = max_tasks + nkeys + 1;
 
     // bucket reduction geometry: level-0 radix (enough chunks to keep every SM sub-partition busy), then the
@@ -1138,6 +1439,17 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const size_t o_heavy = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_multi = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_huge = off;     off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
+    // batched-affine rounds: two offset arrays and two point lists (ping-pong), prefix products, thread products
+    size_t o_aff_off[2] = {0, 0}, o_aff_pts[2] = {0, 0}, o_aff_prefix = 0, o_aff_totals = 0;
+    if (aff_rounds) {
+        const uint64_t threads1 = (aff_entries[1] + aff_m - 1) / aff_m;
+        o_aff_off[0] = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
+        o_aff_off[1] = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
+        o_aff_pts[0] = off;   off = align_up(off + sizeof(G1Affine) * aff_entries[1], 256);
+        o_aff_pts[1] = off;   off = align_up(off + sizeof(G1Affine) * (aff_rounds > 1 ? aff_entries[2] : 0), 256);
+        o_aff_prefix = off;   off = align_up(off + sizeof(Fq) * threads1 * aff_m, 256);
+        o_aff_totals = off;   off = align_up(off + sizeof(Fq) * threads1, 256);
+    }
     // partition sort (large inputs)
     SortGeom sg;
     memset(&sg, 0, sizeof(sg));
@@ -1221,14 +1533,15 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     } else {
         KZG_LAUNCH(ctx, msm_digits_kernel<false>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, counts, nullptr);
     }
-    KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums);
-    KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, offsets);
-    KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, tile_sums,
-               offsets, cursor, heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
-    KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums);
-    KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, segoff);
-    KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, offsets, nkeys, g.seg, tile_sums, segoff, cursor,
-               heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
+    // exclusive scan of ceil(count / 2^shift) over the keys -> out[0 .. nkeys]
+    auto scan_offsets = [&](uint32_t shift, uint32_t* out, uint32_t* cursor_out) {
+        KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, shift,
+                   tile_sums);
+        KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, out);
+        KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, shift,
+                   tile_sums, out, cursor_out, heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
+    };
+    scan_offsets(0, offsets, cursor);
     if (use_part_sort)
         KZG_LAUNCH(ctx, msm_chunk_scatter_kernel, max_chunks, CHUNK_THREADS, CHUNK_SMEM, mid, pstart, cstart, sg, chunk_hist, cursor,
                    sorted);
@@ -1236,9 +1549,51 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
     timed_end(ctx, KZG_TIMED_MSM_SORT);
 
+    // batched-affine rounds: (sorted, offsets) -> dense point lists, half as long each time
+    const uint32_t* walk_offsets = offsets;
+    const G1Affine* walk_points = pts;
+    if (aff_rounds) timed_begin(ctx, KZG_TIMED_MSM_AFFINE);
+    for (uint32_t r = 1; r <= aff_rounds; r++) {
+        uint32_t* off_out = (uint32_t*)(sc + o_aff_off[r & 1]);
+        G1Affine* pts_out = (G1Affine*)(sc + o_aff_pts[(r & 1) ^ 1]);
+        Fq* prefix = (Fq*)(sc + o_aff_prefix);
+        Fq* totals = (Fq*)(sc + o_aff_totals);
+        scan_offsets(r, off_out, cursor);  // (the scatter is done with `cursor`: free scratch)
+        AffRound ar;
+        ar.bases = pts;
+        ar.sorted = r == 1 ? sorted : nullptr;
+        ar.in = r == 1 ? nullptr : walk_points;
+        ar.off_in = walk_offsets;
+        ar.off_out = off_out;
+        ar.nkeys = nkeys;
+        ar.nthreads = (uint32_t)((aff_entries[r] + aff_m - 1) / aff_m);
+        const uint32_t blocks = (ar.nthreads + AFF_THREADS - 1) / AFF_THREADS;
+        if (r == 1)
+            KZG_LAUNCH(ctx, msm_aff_forward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals);
+        else
+            KZG_LAUNCH(ctx, msm_aff_forward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals);
+        KZG_TRY(fq_batch_inverse(ctx, totals, totals, ar.nthreads));
+        if (r == 1)
+            KZG_LAUNCH(ctx, msm_aff_backward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals, pts_out);
+        else
+            KZG_LAUNCH(ctx, msm_aff_backward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals, pts_out);
+        walk_offsets = off_out;
+        walk_points = pts_out;
+    }
+    if (aff_rounds) timed_end(ctx, KZG_TIMED_MSM_AFFINE);
+
+    // partial-sum slots of the XYZZ walk over what is left
+    KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 1, counts, walk_offsets, nkeys, g.seg, aff_rounds, tile_sums);
+    KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, segoff);
+    KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, walk_offsets, nkeys, g.seg, aff_rounds, tile_sums,
+               segoff, cursor, heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
     const uint32_t ablocks = (uint32_t)((max_tasks + 127) / 128);
     timed_begin(ctx, KZG_TIMED_MSM_ACCUMULATE);
-    KZG_LAUNCH(ctx, msm_accumulate_kernel, ablocks, 128, 0, pts, sorted, offsets, segoff, nkeys, g.seg, partials);
+    if (aff_rounds)
+        KZG_LAUNCH(ctx, msm_accumulate_kernel<true>, ablocks, 128, 0, walk_points, (const uint32_t*)nullptr, walk_offsets, segoff,
+                   nkeys, g.seg, partials);
+    else
+        KZG_LAUNCH(ctx, msm_accumulate_kernel<false>, ablocks, 128, 0, pts, sorted, offsets, segoff, nkeys, g.seg, partials);
     timed_end(ctx, KZG_TIMED_MSM_ACCUMULATE);
     timed_begin(ctx, KZG_TIMED_MSM_REDUCE);
     KZG_LAUNCH(ctx, msm_collapse_huge_kernel, 128, 512, 0, partials, segoff, huge + 1, huge);
@@ -1481,6 +1836,16 @@ int kzg_msm_geometry(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uin
     return KZG_OK;
 }
 
+int kzg_msm_plan(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows,
+                 uint32_t* affine_rounds) {
+    if (!ctx) return KZG_ERR_ARG;
+    MsmBases b = srs ? srs_bases(ctx, srs, 0) : raw_bases(nullptr);
+    MsmGeom g = msm_geometry(ctx, b, n ? n : 1, montgomery != 0);
+    if (window_bits) *window_bits = g.c;
+    if (windows) *windows = g.nwin;
+    if (affine_rounds) *affine_rounds = msm_affine_rounds((n ? n : 1) * g.nwin, g.nsets * g.nbuckets);
+    return KZG_OK;
+}
 int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c) {
     if (!ctx) return KZG_ERR_ARG;
     if (c != 0 && (c < 2 || c > 22)) return set_err(ctx, KZG_ERR_ARG, "msm window must be 0 (auto) or in [2, 22]");

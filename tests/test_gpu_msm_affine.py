@@ -1,0 +1,113 @@
+"""Batched-affine bucket rounds of the MSM (csrc/msm.cu: msm_aff_forward / fq_batch_inverse / msm_aff_backward).
+
+The rounds switch themselves on from 2^22 bucket entries; here they are forced on (KZGB200_AFF_ROUNDS) at sizes the
+oracle can check, through the C ABI, for both MSM flavours.  The result replaces G1.multiExpAffine + G1.toAffine
+(reference src/polynomial/polynomial.js:1106-1115) and must be the same canonical affine bytes whatever the number
+of rounds.  Exceptional pairs (operand at infinity, P + P, P + (-P)) get their own SRS.
+"""
+import ctypes as C
+
+import pytest
+
+from oracle.py import bn254 as bn, inputs
+
+pytestmark = pytest.mark.gpu
+R = bn.R
+
+
+def _srs_msm(curve, srs, scalars, n):
+    from kzg_grandsums_study_b200._lib import as_ptr
+    buf = curve.to_device(bn.fr_vec_to_std_bytes(scalars))
+    out = bytearray(64)
+    curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out)))
+    return bytes(out)
+
+
+@pytest.mark.parametrize("flavour,c", [("table", 4), ("table", 9), ("table", 13), ("raw", 5), ("raw", 11)])
+@pytest.mark.parametrize("rounds", ["1", "2", "3", "6"])
+def test_affine_rounds_vs_closed_form(curve, tau, flavour, c, rounds, monkeypatch):
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200._lib import as_ptr
+    n = 2600
+    srs = C.c_void_p()
+    curve.check(curve.lib.kzg_srs_generate(curve.ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
+    try:
+        if flavour == "table":
+            curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, c))
+        else:
+            curve.check(curve.lib.kzg_msm_set_window(curve.ctx, c))
+        scal = synthetic.random_fr_std(6100 + c, n)
+        cases = [[sum(int(scal[i, j]) << (64 * j) for j in range(4)) for i in range(n)],
+                 [5] * n,                                   # one bucket holds everything: a deep pairwise tree
+                 [0] * n,                                   # no entries at all
+                 [R - 1 - (i % 2) for i in range(n)],
+                 [(i % 7) + 1 for i in range(n)]]           # seven buckets, odd and even sizes
+        monkeypatch.setenv("KZGB200_AFF_ROUNDS", rounds)
+        for scalars in cases:
+            expect = sum(s * pow(tau, i, R) for i, s in enumerate(scalars)) % R
+            want = bn.g1_to_bytes(bn.g1_mul_gen(expect))
+            assert _srs_msm(curve, srs, scalars, n) == want, (flavour, c, rounds, scalars[0])
+            mont = curve.to_device(bn.fr_vec_to_mont_bytes(scalars))
+            out = bytearray(64)
+            curve.check(curve.lib.kzg_commit(curve.ctx, srs, mont.handle, as_ptr(out)))
+            assert bytes(out) == want, (flavour, c, rounds, "commit")
+    finally:
+        monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+        curve.check(curve.lib.kzg_msm_set_window(curve.ctx, 0))
+        curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+@pytest.mark.parametrize("rounds", ["1", "2", "4"])
+def test_affine_rounds_exceptional_pairs(curve, rounds, monkeypatch):
+    """an SRS of G, infinity, G, -G repeated: every pair of a bucket is a doubling, a cancellation or has an operand at
+    infinity, and the sums that come out of one round meet again in the next"""
+    from kzg_grandsums_study_b200._lib import as_ptr
+    G = bn.g1_to_bytes((1, 2))
+    negG = bn.g1_to_bytes((1, bn.Q - 2))
+    inf = bytes(64)
+    n = 1200
+    layouts = [((G + inf + G + negG) * 300, [1, 0, 1, -1] * 300),
+               (G * n, [1] * n),                             # nothing but doublings, level after level
+               ((G + negG) * 600, [1, -1] * 600),            # nothing but cancellations
+               ((inf + inf + G) * 400, [0, 0, 1] * 400)]
+    for pts, coeffs in layouts:
+        srs = C.c_void_p()
+        curve.check(curve.lib.kzg_srs_from_host(curve.ctx, as_ptr(pts), n, C.byref(srs)))
+        try:
+            for table_c in (0, 5):
+                curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, table_c))
+                monkeypatch.setenv("KZGB200_AFF_ROUNDS", rounds)
+                for scalars in ([7] * n, inputs.random_column(3, n), [R - 1] * n, [(i % 5) + 1 for i in range(n)]):
+                    expect = sum(s * c for s, c in zip(scalars, coeffs)) % R
+                    assert _srs_msm(curve, srs, scalars, n) == bn.g1_to_bytes(bn.g1_mul_gen(expect)), (table_c, scalars[0])
+                monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+        finally:
+            monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+            curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+@pytest.mark.parametrize("log_n", [18, 20])
+def test_affine_rounds_match_the_xyzz_walk(curve, tau, log_n, monkeypatch):
+    """at sizes where the rounds are on by default (2^20: 13.6 M entries) and forced at 2^18: same bytes as the plain
+    XYZZ walk (KZGB200_AFF_ROUNDS=0) and as the closed form p(tau) G1"""
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200._lib import as_ptr
+    from kzg_grandsums_study_b200.polynomial import Polynomial
+    n = 1 << log_n
+    srs = C.c_void_p()
+    curve.check(curve.lib.kzg_srs_generate(curve.ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
+    try:
+        p = Polynomial(synthetic.random_fr_std(91 + log_n, n).tobytes(), curve)
+        p_tau = bn.fr_from_mont_bytes(p.evaluate(bn.fr_to_mont_bytes(tau)))
+        want = bn.g1_to_bytes(bn.g1_mul_gen(p_tau))
+        got = {}
+        for rounds in ("0", "2", "4", None):
+            if rounds is None:
+                monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+            else:
+                monkeypatch.setenv("KZGB200_AFF_ROUNDS", rounds)
+            got[rounds] = p.multiExponentiation(srs)
+        assert all(v == want for v in got.values()), {k: v == want for k, v in got.items()}
+    finally:
+        monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+        curve.lib.kzg_srs_free(curve.ctx, srs)

@@ -18,7 +18,7 @@ torch.cuda.set_stream(_stream)
 curve = Curve(0, _stream.cuda_stream)
 lib, ctx = curve.lib, curve.ctx
 tau = synthetic.tau_from_seed(1001)
-TAGS = (("sort", 2), ("accumulate", 0), ("reduce", 3), ("finish", 4))
+TAGS = (("sort", 2), ("affine", 5), ("accumulate", 0), ("reduce", 3), ("finish", 4))
 for log_n in sizes:
     n = 1 << log_n
     srs = C.c_void_p()
