@@ -702,6 +702,13 @@ __device__ __forceinline__ G1Affine aff_load_point(const AffRound& a, uint32_t h
     if (neg) p.y = fp_neg(p.y);
     return p;
 }
+// the same without the sign: a prefetch must not touch what it loads (the first use of a loaded register is where
+// the warp waits), so the software pipeline of msm_aff_backward applies the sign when the point is consumed
+template <bool INDEXED>
+__device__ __forceinline__ G1Affine aff_request_point(const AffRound& a, uint32_t h) {
+    uint32_t neg;
+    return load_affine(aff_operand<INDEXED>(a, h, neg));
+}
 // kind of the pair and the denominator it contributes to the batch
 __device__ __forceinline__ int aff_classify(const G1Affine& p1, const G1Affine& p2, Fq& d) {
     d = fp_one<FqP>();
@@ -842,37 +849,40 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRou
     const uint32_t end = (uint32_t)min((uint64_t)total, begin64 + m);
     Fq s = load_fq_ldg(inv_totals + t);  // 1 / (d_0 ... d_j) while pair j is being finished
     // Software pipeline, one output deep: the operands and the prefix product of output o - 1 are requested before the
-    // addition of output o is computed.  (Measured on B200 at 2^22 points: a second stage for the handles changed
-    // nothing, a third one with prefetch.global.L2 for the operands made round 1 20 % slower.)
+    // addition of output o is computed, and not touched until then (the signs of round 1 are applied at use: with
+    // fp_neg inside the prefetch the warp waited for the gather right there, 40 % of all stall samples).
+    // (Measured: a second stage that fetches the handles of output o - 2 costs more in registers than it hides.)
     AffCursor c = aff_seek(a, end - 1);
-    uint32_t h1, h2;
+    uint32_t h1, h2, nh1 = 0, nh2 = 0;
     bool pair;
     G1Affine p1, p2;
     Fq pre;
     aff_handles<INDEXED>(a, c, end - 1, h1, h2, pair);
     const Fq* pre_ptr = prefix + (uint64_t)(end - 1 - begin) * a.nthreads + t;
-    p1 = aff_load_point<INDEXED>(a, h1);
+    p1 = aff_request_point<INDEXED>(a, h1);
     if (pair) {
-        p2 = aff_load_point<INDEXED>(a, h2);
+        p2 = aff_request_point<INDEXED>(a, h2);
         pre = load_fq_ldg(pre_ptr);
     }
 #pragma unroll 1
     for (uint32_t o = end - 1;; o--, pre_ptr -= a.nthreads) {
         const bool more = o > begin;
-        bool q_pair = false;  // (o - 1)
+        bool npair = false;  // (o - 1)
         G1Affine n1, n2;
         Fq npre;
         if (more) {
             aff_step_down(a, c, o - 1);
-            aff_handles<INDEXED>(a, c, o - 1, h1, h2, q_pair);
-            n1 = aff_load_point<INDEXED>(a, h1);
-            if (q_pair) {
-                n2 = aff_load_point<INDEXED>(a, h2);
+            aff_handles<INDEXED>(a, c, o - 1, nh1, nh2, npair);
+            n1 = aff_request_point<INDEXED>(a, nh1);
+            if (npair) {
+                n2 = aff_request_point<INDEXED>(a, nh2);
                 npre = load_fq_ldg(pre_ptr - a.nthreads);
             }
         }
         G1Affine r = p1;
+        if (INDEXED && (h1 >> 31)) r.y = fp_neg(r.y);
         if (pair) {
+            if (INDEXED && (h2 >> 31)) p2.y = fp_neg(p2.y);
             Fq d;
             const int kind = aff_classify(r, p2, d);
             const Fq inv = fp_mul(s, pre);
@@ -899,7 +909,9 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRou
         p1 = n1;
         p2 = n2;
         pre = npre;
-        pair = q_pair;
+        pair = npair;
+        h1 = nh1;
+        h2 = nh2;
     }
 }
 

@@ -1,7 +1,7 @@
 """Batched-affine bucket rounds of the MSM (csrc/msm.cu: msm_aff_forward / fq_batch_inverse / msm_aff_backward).
 
-The rounds switch themselves on from 2^22 bucket entries; here they are forced on (KZGB200_AFF_ROUNDS) at sizes the
-oracle can check, through the C ABI, for both MSM flavours.  The result replaces G1.multiExpAffine + G1.toAffine
+The rounds switch themselves on from 2^22 points (48 M bucket entries); here they are forced on (KZGB200_AFF_ROUNDS)
+at sizes the oracle can check, through the C ABI, for both MSM flavours.  The result replaces G1.multiExpAffine + G1.toAffine
 (reference src/polynomial/polynomial.js:1106-1115) and must be the same canonical affine bytes whatever the number
 of rounds.  Exceptional pairs (operand at infinity, P + P, P + (-P)) get their own SRS.
 """
@@ -88,8 +88,8 @@ def test_affine_rounds_exceptional_pairs(curve, rounds, monkeypatch):
 
 @pytest.mark.parametrize("log_n", [18, 20])
 def test_affine_rounds_match_the_xyzz_walk(curve, tau, log_n, monkeypatch):
-    """at sizes where the rounds are on by default (2^20: 13.6 M entries) and forced at 2^18: same bytes as the plain
-    XYZZ walk (KZGB200_AFF_ROUNDS=0) and as the closed form p(tau) G1"""
+    """forced rounds over millions of entries (multi-level batch inversion, the partition sort in front): same bytes as
+    the plain XYZZ walk (KZGB200_AFF_ROUNDS=0), as the library's own choice, and as the closed form p(tau) G1"""
     from kzg_grandsums_study_b200 import synthetic
     from kzg_grandsums_study_b200._lib import as_ptr
     from kzg_grandsums_study_b200.polynomial import Polynomial

@@ -2,6 +2,9 @@
 
   python tools/summarize_profiles.py launches <csv> <out.md> <title> [last_n]
   python tools/summarize_profiles.py full <ncu-rep> <out.md> <title>
+  python tools/summarize_profiles.py multi <csv> <out.md> <title> <first kernel of the sequence to keep>
+      (csv of `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
+       sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed --csv`: one row per launch and metric)
 """
 import collections
 import csv
@@ -32,6 +35,42 @@ def launches(path, out, title, last_n=None):
         f.write("\nLaunch order (last sequence):\n\n```\n")
         for r in rows:
             f.write("%-64s %10.3f ms\n" % (r[4][:64], float(r[-1]) / 1e6))
+        f.write("```\n")
+
+
+def multi(path, out, title, first_kernel):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    ix = {h: i for i, h in enumerate(rows[0])}
+    data = collections.OrderedDict()
+    for r in rows[1:]:
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("kzg::", "").strip()
+        data.setdefault((int(r[ix["ID"]]), name), {})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
+    items = list(data.items())
+    starts = [i for i, ((_, k), _m) in enumerate(items) if k.startswith(first_kernel)]
+    seq = items[starts[-1]:]
+    T, RD, WR, FM = "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", \
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"
+    total = sum(m[T] for _, m in seq) / 1e6
+    agg = collections.OrderedDict()
+    for (_, k), m in seq:
+        a = agg.setdefault(k, [0, 0.0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += m[T] / 1e6
+        a[2] += m[RD]
+        a[3] += m[WR]
+        a[4] += m[FM] * m[T]
+    with open(out, "w") as f:
+        f.write("# %s\n\n" % title)
+        f.write("Source: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fmaheavy_cycles_active"
+                " --clock-control none` (per-launch times are cold-cache and serialised: compare SHARES, not absolutes).  "
+                "%d launches, %.3f ms in total.\n\n" % (len(seq), total))
+        f.write("| kernel | launches | total ms | share | DRAM read GB | DRAM written GB | fmaheavy % (time-weighted) |\n|---|---:|---:|---:|---:|---:|---:|\n")
+        for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write("| `%s` | %d | %.3f | %.1f %% | %.2f | %.2f | %.1f |\n" % (k, v[0], v[1], 100 * v[1] / total, v[2] / 1e9, v[3] / 1e9,
+                                                                          v[4] / (v[1] * 1e6) if v[1] else 0))
+        f.write("\nLaunch order:\n\n```\n")
+        for (_, k), m in seq:
+            f.write("%-34s %9.3f ms  fmaheavy %5.1f %%  DRAM read %8.1f MB  written %8.1f MB\n" % (k[:34], m[T] / 1e6, m[FM], m[RD] / 1e6, m[WR] / 1e6))
         f.write("```\n")
 
 
@@ -72,6 +111,9 @@ def full(path, out, title):
             f.write("\n")
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "multi":
+    multi(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
+    sys.exit(0)
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(*sys.argv[2:])
