@@ -35,6 +35,7 @@ struct kzg_ctx {
     // other one's bucket accumulation).  msm.cu's MsmLane swaps `stream` / the scratch arena for the duration of a
     // call, so every launch macro keeps using ctx->stream.
     cudaStream_t aux_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host-scalar MSMs: the piecewise upload, so that both lanes can compute under it
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int lane = 0;
     bool no_split = false;  // KZGB200_NO_SPLIT=1: mid-sized MSMs are not split over the two lanes (A/B timing)

@@ -235,6 +235,7 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
         ctx->own_stream = true;
     }
     if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
@@ -291,6 +292,10 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
     for (auto& t : ctx->coset_tables) cudaFree(t.inv_nx);
     cudaFree(ctx->scratch);
     cudaFree(ctx->scratch2);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     if (ctx->aux_stream) {
         cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamDestroy(ctx->aux_stream);

@@ -1689,7 +1689,13 @@ __global__ void g1_add2_kernel(const G1XYZZ* __restrict__ parts, G1XYZZ* __restr
 // Measured on B200: pays only around 2^23 points (21.2 vs 21.8 ms) -- below that the second bucket reduction (its
 // cost is per bucket, not per point) eats the overlap (2^20: 3.97 vs 3.71 ms), above it the tail is negligible.
 int msm_run_split(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev) {
-    if (n <= (1ull << 22) || n > (1ull << 23) || ctx->lane != 0 || ctx->no_split) return msm_run(ctx, bases, src, n, result_dev);
+    // Two halves on the two lanes (the latency-bound tail of one under the accumulation of the other) won 3 % around
+    // 2^23 points before the batched-affine rounds; with them one undivided MSM is faster everywhere (2^23: 18.5 vs
+    // 20.0 ms, 2^24: 33.7 vs 35.7 ms, 2^22: 9.8 vs 11.1 ms), so the range is empty unless set for an experiment.
+    uint64_t split_min = 0, split_max = 0;  // split when split_min < n <= split_max
+    if (const char* ov = getenv("KZGB200_SPLIT_MIN_LOG")) split_min = 1ull << atoi(ov);  // tuning / A-B tests
+    if (const char* ov = getenv("KZGB200_SPLIT_MAX_LOG")) split_max = 1ull << atoi(ov);
+    if (n <= split_min || n > split_max || ctx->lane != 0 || ctx->no_split) return msm_run(ctx, bases, src, n, result_dev);
     const uint64_t h = n / 2;
     G1XYZZ* halves = (G1XYZZ*)(ctx->dev_small + 12288);
     cudaStream_t main_stream = ctx->stream;
@@ -1933,25 +1939,38 @@ int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* sca
             cut[1] = n / 16 * 3;
             cut[2] = n;
         }
+        // All uploads are queued at once on the copy stream.  Piece k runs on lane k & 1 (own stream, own scratch arena)
+        // and waits only for its own upload, so the next piece starts sorting while the latency-bound tail of the
+        // previous one (bucket reduction, the inversions of the affine rounds) is still running.
         cudaEvent_t up[3] = {nullptr, nullptr, nullptr};
         for (uint32_t k = 0; k < parts; k++) cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming);
-        cudaError_t e = cudaEventRecord(ctx->ev_fork, ctx->stream);  // tmp exists from here on
+        cudaStream_t main_stream = ctx->stream;
+        cudaError_t e = cudaEventRecord(ctx->ev_fork, main_stream);  // tmp exists from here on
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0);
         for (uint32_t k = 0; k < parts && e == cudaSuccess; k++) {
             e = cudaMemcpyAsync(tmp + cut[k], host + cut[k], sizeof(Fr) * (cut[k + 1] - cut[k]), cudaMemcpyHostToDevice,
-                                ctx->aux_stream);
-            if (e == cudaSuccess) e = cudaEventRecord(up[k], ctx->aux_stream);
+                                ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(up[k], ctx->copy_stream);
         }
         if (e != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, std::string("msm upload: ") + cudaGetErrorString(e));
+        const bool lanes = ctx->lane == 0 && !ctx->no_split;
         for (uint32_t k = 0; k < parts && r == KZG_OK; k++) {
+            const int lane = lanes ? (int)(k & 1) : 0;
+            ctx->lane = lane;
+            ctx->stream = lane ? ctx->aux_stream : main_stream;
             cudaStreamWaitEvent(ctx->stream, up[k], 0);
             r = msm_run(ctx, srs_bases(ctx, srs, first + cut[k]), MsmScalarSrc{tmp + cut[k], false}, cut[k + 1] - cut[k], slots + k);
         }
-        // (also on the error path: tmp is freed on the main stream, after every upload that was queued)
+        ctx->lane = 0;
+        ctx->stream = main_stream;
+        // (also on the error path: tmp is freed on the main stream, after every upload and every piece that was queued)
+        cudaEventRecord(ctx->ev_join, ctx->copy_stream);
+        cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
         cudaEventRecord(ctx->ev_join, ctx->aux_stream);
-        cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+        cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
         if (r == KZG_OK) r = msm_result_to_host_affine(ctx, slots, parts, out_affine);
-        else cudaStreamSynchronize(ctx->stream);
+        else cudaStreamSynchronize(main_stream);
         for (uint32_t k = 0; k < parts; k++) cudaEventDestroy(up[k]);
     } else {
         if (n) KZG_CUDA(ctx, cudaMemcpyAsync(tmp, host, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
