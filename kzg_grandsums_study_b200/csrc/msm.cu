@@ -568,6 +568,28 @@ __global__ void __launch_bounds__(CHUNK_THREADS) msm_chunk_scatter_kernel(const 
 // ---------------------------------------------------------------------------------------------
 // bucket accumulation
 // ---------------------------------------------------------------------------------------------
+// Random gathers from the multi-GiB window table (tools/micro/gather.cu, B200): a plain load that misses makes the L2
+// fetch the whole 128-byte line (127 B of DRAM traffic per 32- or 64-byte gather); with the .L2::64B qualifier it
+// fetches 64 B.  The RATE is the same either way -- ~44 G random 32-byte sectors per second, a 64-byte point costs two
+// -- but half the DRAM bandwidth stays free for the streaming traffic of the same kernels.
+__device__ __forceinline__ uint4 ldg_gather16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ Fq load_fq_gather(const Fq* p) {
+    Fq r;
+    const uint4 a = ldg_gather16(p), b = ldg_gather16(reinterpret_cast<const uint4*>(p) + 1);
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ G1Affine load_affine_gather(const G1Affine* p) {
+    G1Affine r;
+    r.x = load_fq_gather(&p->x);
+    r.y = load_fq_gather(&p->y);
+    return r;
+}
 __device__ __forceinline__ G1Affine load_affine(const G1Affine* p) {
     G1Affine r;
     const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -621,7 +643,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
 
     G1XYZZ acc = xyzz_inf();
     uint32_t e = DIRECT ? begin : sorted[begin];
-    G1Affine p = load_affine(bases + (DIRECT ? e : e & 0x7fffffffu));
+    G1Affine p = DIRECT ? load_affine(bases + e) : load_affine_gather(bases + (e & 0x7fffffffu));
     for (uint32_t j = begin; j < end; j++) {
         if (j == key_end) {  // bucket boundary inside the slice
             store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
@@ -636,7 +658,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
         G1Affine p_next = p;
         if (j + 1 < end) {
             e_next = DIRECT ? j + 1 : sorted[j + 1];
-            p_next = load_affine(bases + (DIRECT ? e_next : e_next & 0x7fffffffu));
+            p_next = DIRECT ? load_affine(bases + e_next) : load_affine_gather(bases + (e_next & 0x7fffffffu));
         }
         if (!DIRECT && (e >> 31)) p.y = fp_neg(p.y);
         xyzz_madd(acc, p);
@@ -698,7 +720,7 @@ template <bool INDEXED>
 __device__ __forceinline__ G1Affine aff_load_point(const AffRound& a, uint32_t h) {
     uint32_t neg;
     const G1Affine* q = aff_operand<INDEXED>(a, h, neg);
-    G1Affine p = load_affine(q);
+    G1Affine p = INDEXED ? load_affine_gather(q) : load_affine(q);
     if (neg) p.y = fp_neg(p.y);
     return p;
 }
@@ -707,7 +729,17 @@ __device__ __forceinline__ G1Affine aff_load_point(const AffRound& a, uint32_t h
 template <bool INDEXED>
 __device__ __forceinline__ G1Affine aff_request_point(const AffRound& a, uint32_t h) {
     uint32_t neg;
-    return load_affine(aff_operand<INDEXED>(a, h, neg));
+    const G1Affine* q = aff_operand<INDEXED>(a, h, neg);
+    return INDEXED ? load_affine_gather(q) : load_affine(q);
+}
+// both operands of output o's pair
+template <bool INDEXED>
+__device__ __forceinline__ void aff_request_pair(const AffRound& a, uint32_t o, uint32_t h1, uint32_t h2, G1Affine& p1, G1Affine& p2) {
+    // (Measured: letting the forward pass of round 1 save the x coordinates so that this one gathers only the y halves
+    // costs more in the forward pass -- 6.4 GB of extra stores at 2^24 points, 5.0 -> 6.3 ms -- than it saves here,
+    // 9.7 -> 9.6 ms: the backward pass is not bound by its gathers.)
+    p1 = aff_request_point<INDEXED>(a, h1);
+    p2 = aff_request_point<INDEXED>(a, h2);
 }
 // kind of the pair and the denominator it contributes to the batch
 __device__ __forceinline__ int aff_classify(const G1Affine& p1, const G1Affine& p2, Fq& d) {
@@ -777,6 +809,13 @@ __device__ __forceinline__ void aff_step_down(const AffRound& a, AffCursor& c, u
 }
 
 template <bool INDEXED>
+__device__ __forceinline__ Fq aff_load_x(const AffRound& a, uint32_t h) {
+    uint32_t neg;
+    const Fq* x = &aff_operand<INDEXED>(a, h, neg)->x;
+    return INDEXED ? load_fq_gather(x) : load_fq_ldg(x);
+}
+
+template <bool INDEXED>
 __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRound a, uint32_t m, Fq* __restrict__ prefix,
                                                                          Fq* __restrict__ totals) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -788,13 +827,13 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRoun
         const uint32_t begin = (uint32_t)begin64;
         const uint32_t end = (uint32_t)min((uint64_t)total, begin64 + m);
         AffCursor c = aff_seek(a, begin);
-        uint32_t h1, h2, neg;
+        uint32_t h1, h2;
         bool pair;
         Fq x1, x2;  // x coordinates of the pair in hand, fetched one iteration ahead
         aff_handles<INDEXED>(a, c, begin, h1, h2, pair);
         if (pair) {
-            x1 = load_fq_ldg(&aff_operand<INDEXED>(a, h1, neg)->x);
-            x2 = load_fq_ldg(&aff_operand<INDEXED>(a, h2, neg)->x);
+            x1 = aff_load_x<INDEXED>(a, h1);
+            x2 = aff_load_x<INDEXED>(a, h2);
         }
         Fq* pre = prefix + t;
 #pragma unroll 1
@@ -806,8 +845,8 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRoun
                 aff_step_up(a, c, o + 1);
                 aff_handles<INDEXED>(a, c, o + 1, nh1, nh2, npair);
                 if (npair) {
-                    nx1 = load_fq_ldg(&aff_operand<INDEXED>(a, nh1, neg)->x);
-                    nx2 = load_fq_ldg(&aff_operand<INDEXED>(a, nh2, neg)->x);
+                    nx1 = aff_load_x<INDEXED>(a, nh1);
+                    nx2 = aff_load_x<INDEXED>(a, nh2);
                 }
             }
             if (pair) {
@@ -859,10 +898,11 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRou
     Fq pre;
     aff_handles<INDEXED>(a, c, end - 1, h1, h2, pair);
     const Fq* pre_ptr = prefix + (uint64_t)(end - 1 - begin) * a.nthreads + t;
-    p1 = aff_request_point<INDEXED>(a, h1);
     if (pair) {
-        p2 = aff_request_point<INDEXED>(a, h2);
+        aff_request_pair<INDEXED>(a, end - 1, h1, h2, p1, p2);
         pre = load_fq_ldg(pre_ptr);
+    } else {
+        p1 = aff_request_point<INDEXED>(a, h1);
     }
 #pragma unroll 1
     for (uint32_t o = end - 1;; o--, pre_ptr -= a.nthreads) {
@@ -873,10 +913,11 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRou
         if (more) {
             aff_step_down(a, c, o - 1);
             aff_handles<INDEXED>(a, c, o - 1, nh1, nh2, npair);
-            n1 = aff_request_point<INDEXED>(a, nh1);
             if (npair) {
-                n2 = aff_request_point<INDEXED>(a, nh2);
+                aff_request_pair<INDEXED>(a, o - 1, nh1, nh2, n1, n2);
                 npre = load_fq_ldg(pre_ptr - a.nthreads);
+            } else {
+                n1 = aff_request_point<INDEXED>(a, nh1);
             }
         }
         G1Affine r = p1;
