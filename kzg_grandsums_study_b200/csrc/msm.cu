@@ -1979,6 +1979,15 @@ int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* sca
             parts = 2;
             cut[1] = n / 16 * 3;
             cut[2] = n;
+            if (const char* ov = getenv("KZGB200_HOST_PIECES")) {  // tuning: "a,b" = cuts at a/64 and b/64 of n (b = 64: two pieces)
+                int a = 0, b = 64;
+                if (sscanf(ov, "%d,%d", &a, &b) >= 1 && a > 0 && a < b && b <= 64) {
+                    cut[1] = n / 64 * a;
+                    cut[2] = b < 64 ? n / 64 * b : n;
+                    cut[3] = n;
+                    parts = b < 64 ? 3 : 2;
+                }
+            }
         }
         // All uploads are queued at once on the copy stream.  Piece k runs on lane k & 1 (own stream, own scratch arena)
         // and waits only for its own upload, so the next piece starts sorting while the latency-bound tail of the

@@ -111,3 +111,21 @@ def test_affine_rounds_match_the_xyzz_walk(curve, tau, log_n, monkeypatch):
     finally:
         monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
         curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+def test_msm_plan_reports_the_rounds(curve, monkeypatch):
+    """kzg_msm_plan: what an n-point MSM will do -- no rounds for small inputs, some for 2^24 points, and the override"""
+    c, w, r = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+    for n, want in ((1, 0), (1 << 16, 0), (1 << 20, 0)):
+        curve.check(curve.lib.kzg_msm_plan(curve.ctx, None, n, 0, C.byref(c), C.byref(w), C.byref(r)))
+        assert r.value == want and w.value == -(-257 // c.value), (n, c.value, w.value, r.value)
+    curve.check(curve.lib.kzg_msm_plan(curve.ctx, None, 1 << 24, 0, C.byref(c), C.byref(w), C.byref(r)))
+    assert 1 <= r.value <= 6
+    g_c, g_w = C.c_uint32(), C.c_uint32()
+    curve.check(curve.lib.kzg_msm_geometry(curve.ctx, None, 1 << 24, 0, C.byref(g_c), C.byref(g_w)))
+    assert (g_c.value, g_w.value) == (c.value, w.value)
+    monkeypatch.setenv("KZGB200_AFF_ROUNDS", "2")
+    curve.check(curve.lib.kzg_msm_plan(curve.ctx, None, 1000, 1, C.byref(c), C.byref(w), C.byref(r)))
+    assert r.value == 2 and w.value == -(-255 // c.value)
+    monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
