@@ -129,3 +129,29 @@ def test_msm_plan_reports_the_rounds(curve, monkeypatch):
     curve.check(curve.lib.kzg_msm_plan(curve.ctx, None, 1000, 1, C.byref(c), C.byref(w), C.byref(r)))
     assert r.value == 2 and w.value == -(-255 // c.value)
     monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+
+
+@pytest.mark.parametrize("kind", ["gs", "gp"])
+@pytest.mark.parametrize("rounds", ["1", "3"])
+def test_whole_proofs_with_forced_rounds(kind, rounds, curve, tau, ptau_factory, monkeypatch):
+    """every commitment of a proof through the affine rounds (both lanes of the prover, Montgomery-source scalars):
+    the proof stays byte-identical to the oracle's (reference src/grandsum|grandproduct/mset_eq_kzg_prover.js)"""
+    from kzg_grandsums_study_b200.grandproduct import mset_eq_kzg_grandproduct_prover
+    from kzg_grandsums_study_b200.grandsum import mset_eq_kzg_grandsum_prover
+    from kzg_grandsums_study_b200.polynomial import Evaluations
+    from oracle.py import protocol as pr
+    nbits = 9
+    n = 1 << nbits
+    path = ptau_factory(nbits)
+    f = inputs.random_column(40 + int(rounds), n)
+    t = inputs.rotate_right(f)
+    fb, tb = bn.fr_vec_to_std_bytes(f), bn.fr_vec_to_std_bytes(t)
+    gpu = mset_eq_kzg_grandsum_prover if kind == "gs" else mset_eq_kzg_grandproduct_prover
+    cpu = pr.grandsum_prover if kind == "gs" else pr.grandproduct_prover
+    want = cpu(pr.TrapdoorSrs(tau, nbits), [fb], [tb])
+    monkeypatch.setenv("KZGB200_AFF_ROUNDS", rounds)
+    try:
+        got = gpu(path, Evaluations(fb, curve), Evaluations(tb, curve))
+    finally:
+        monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+    assert pr.proof_bytes(got) == pr.proof_bytes(want)
