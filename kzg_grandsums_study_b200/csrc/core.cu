@@ -167,7 +167,8 @@ __global__ void selftest_kernel(uint32_t n, unsigned int* fail) {
     if ((i & 63) == 0) {
         Fq a = random_fp<FqP>(s);
         if (!fp_is_zero(a)) ok &= fp_eq(fp_mul(a, fp_inv(a)), fp_one<FqP>());
-        ok &= fp_eq(fp_inv(a), fp_inv_fermat(a));  // binary extended Euclid == a^(p-2)
+        ok &= fp_eq(fp_inv(a), fp_inv_fermat(a));  // binary GCD (31 steps per update) == a^(p-2)
+        ok &= fp_eq(fp_inv_euclid(a), fp_inv_fermat(a));  // plain binary extended Euclid (the fallback)
         Fr b = random_fp<FrP>(s);
         ok &= fp_eq(fp_inv(b), fp_inv_fermat(b));
         ok &= fp_is_zero(fp_inv(fp_zero<FrP>())) && fp_eq(fp_inv(fp_one<FqP>()), fp_one<FqP>());

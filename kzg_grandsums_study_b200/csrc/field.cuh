@@ -509,7 +509,7 @@ KZG_HD void u256_shr1(U256& a, uint32_t top) {
 
 // a^-1 for a Montgomery residue a (inv(0) = 0): X = (aR)^-1 as an integer by the binary extended Euclidean
 // algorithm, then one Montgomery product with R^3 turns a^-1 R^-1 into a^-1 R.
-template <class P> KZG_HD Fp<P> fp_inv(const Fp<P>& a) {
+template <class P> KZG_HD Fp<P> fp_inv_euclid(const Fp<P>& a) {
     if (fp_is_zero(a)) return a;
     U256 u, v, x1, x2, p;
 #pragma unroll
@@ -549,6 +549,226 @@ template <class P> KZG_HD Fp<P> fp_inv(const Fp<P>& a) {
     // R^3 = mont(R^2, R^2) * R ... : mont_mul(R^2, R^2) = R^3
     const Fp<P> r3 = fp_mul(fp_r2<P>(), fp_r2<P>());
     return fp_mul(r, r3);
+}
+
+
+// ---- binary GCD with 31 steps per multi-limb update (Pornin, "Optimized Binary GCD for Modular Inversion",
+// eprint 2020/972, algorithm 2 with k = 32; variable time) -------------------------------------------------
+// The Euclid loop above touches all eight limbs of four numbers in every one of its ~380 steps; for the single lane
+// that runs it (projective -> affine at the end of every MSM, the bottom of every batch inversion) that is ~100 us
+// of dependent instructions.  Here 31 steps at a time run on 64-bit APPROXIMATIONS of a and b (their low 31 bits,
+// which decide the parities exactly, and their top 33 bits, which decide the comparisons almost always) and only
+// record the 2x2 matrix (f0 g0; f1 g1) of what they did; the matrix is then applied once to the full numbers:
+//     (a, b) <- (a f0 + b g0, a f1 + b g1) / 2^31            exact division; a wrong comparison shows up as a
+//                                                             negative result and is fixed by negating the row
+//     (u, v) <- (u f0 + v g0, u f1 + v g1) / 2^31  mod p     one 31-bit Montgomery reduction step each
+// with the invariants a = u y, b = v y (mod p), b odd.  When a reaches 0, b = gcd = 1 and v = 1 / y.
+struct BgRow {
+    uint32_t f, g;  // magnitudes, <= 2^31
+    bool fneg, gneg;
+};
+// out (9 limbs) = x * f
+KZG_HD void bg_mul_small(const uint32_t* x, uint32_t f, uint32_t* out) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)x[i] * f;
+        out[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    out[8] = (uint32_t)c;
+}
+// |x f + y g| >> 31 for signed (f, g) -> out (8 limbs); returns true if x f + y g was negative
+KZG_HD bool bg_combine(const uint32_t* x, const uint32_t* y, const BgRow& r, uint32_t* out) {
+    uint32_t X[9], Y[9];
+    bg_mul_small(x, r.f, X);
+    bg_mul_small(y, r.g, Y);
+    bool neg = r.fneg;
+    if (r.fneg == r.gneg) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            c += (uint64_t)X[i] + Y[i];
+            X[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    } else {
+        uint64_t bw = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            uint64_t d = (uint64_t)X[i] - Y[i] - bw;
+            X[i] = (uint32_t)d;
+            bw = (d >> 32) & 1;
+        }
+        if (bw) {  // |Y| > |X|: the sign is g's, the magnitude the two's complement
+            neg = r.gneg;
+            uint64_t c = 1;
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                c += (uint64_t)(~X[i]);
+                X[i] = (uint32_t)c;
+                c >>= 32;
+            }
+        }
+    }
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        out[i] = (X[i] >> 31) | (X[i + 1] << 1);
+        nz |= out[i];
+    }
+    return neg && nz != 0;
+}
+// (u f + v g) / 2^31 mod p for signed (f, g), u, v in [0, p)
+template <class P> KZG_HD void bg_combine_mod(const uint32_t* u, const uint32_t* v, const BgRow& r, uint32_t* out) {
+    uint32_t us[8], vs[8], X[9], Y[9];
+    {  // a negative factor: use p - u (0 stays 0)
+        uint32_t nzu = 0, nzv = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            nzu |= u[i];
+            nzv |= v[i];
+        }
+        uint64_t bu = 0, bv = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t du = (uint64_t)P::mod(i) - u[i] - bu;
+            uint64_t dv = (uint64_t)P::mod(i) - v[i] - bv;
+            bu = (du >> 32) & 1;
+            bv = (dv >> 32) & 1;
+            us[i] = (r.fneg && nzu) ? (uint32_t)du : u[i];
+            vs[i] = (r.gneg && nzv) ? (uint32_t)dv : v[i];
+        }
+    }
+    bg_mul_small(us, r.f, X);
+    bg_mul_small(vs, r.g, Y);
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {  // < p 2^31 since f + g <= 2^31
+        c += (uint64_t)X[i] + Y[i];
+        X[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    const uint32_t q = (X[0] * P::INV) & 0x7fffffffu;  // X + q p = 0 mod 2^31
+    c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)q * P::mod(i) + X[i];
+        X[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    X[8] += (uint32_t)c;
+    uint32_t t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = (X[i] >> 31) | (X[i + 1] << 1);  // < 2 p
+    const Fp<P> red = fp_final_sub<P>(t);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = red.l[i];
+}
+// bit length of an 8-limb number
+KZG_HD uint32_t bg_clz32(uint32_t w) {  // w != 0
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)w);
+#else
+    return (uint32_t)__builtin_clz(w);
+#endif
+}
+KZG_HD uint32_t bg_len(const uint32_t* x) {
+    uint32_t len = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (x[i]) len = 32 * i + 32 - bg_clz32(x[i]);
+    return len;
+}
+// low 31 bits + the 33 bits below bit n (n >= 64) of an 8-limb number, as one 64-bit word
+KZG_HD uint64_t bg_approx(const uint32_t* x, uint32_t n) {
+    const uint32_t s = n - 33, idx = s >> 5, off = s & 31;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {  // (no dynamic indexing: the limbs stay in registers on the device)
+        if ((uint32_t)i == idx) w0 = x[i];
+        if ((uint32_t)i == idx + 1) w1 = x[i];
+        if ((uint32_t)i == idx + 2) w2 = x[i];
+    }
+    uint64_t top = (((uint64_t)w1 << 32) | w0) >> off;
+    if (off) top |= (uint64_t)w2 << (64 - off);
+    top &= (1ull << 33) - 1;
+    return (top << 31) | (x[0] & 0x7fffffffu);
+}
+
+// a^-1 for a Montgomery residue a (inv(0) = 0): X = (aR)^-1 as an integer, then one Montgomery product with R^3
+// turns a^-1 R^-1 into a^-1 R.
+template <class P> KZG_HD Fp<P> fp_inv(const Fp<P>& y) {
+    if (fp_is_zero(y)) return y;
+    uint32_t a[8], b[8], u[8], v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = y.l[i];
+        b[i] = P::mod(i);
+        u[i] = i == 0 ? 1u : 0u;
+        v[i] = 0u;
+    }
+    for (int iter = 0; iter < 40; iter++) {
+        uint32_t nza = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) nza |= a[i];
+        if (!nza) break;
+        uint32_t n = bg_len(a), nb = bg_len(b);
+        if (nb > n) n = nb;
+        if (n < 64) n = 64;
+        uint64_t abar = bg_approx(a, n), bbar = bg_approx(b, n);
+        int64_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+        for (int j = 0; j < 31; j++) {
+            if (abar & 1) {
+                if (abar < bbar) {
+                    uint64_t tt = abar; abar = bbar; bbar = tt;
+                    int64_t tf = f0; f0 = f1; f1 = tf;
+                    int64_t tg = g0; g0 = g1; g1 = tg;
+                }
+                abar -= bbar;
+                f0 -= f1;
+                g0 -= g1;
+            }
+            abar >>= 1;
+            f1 <<= 1;
+            g1 <<= 1;
+        }
+        BgRow r0, r1;
+        r0.fneg = f0 < 0; r0.f = (uint32_t)(r0.fneg ? -f0 : f0);
+        r0.gneg = g0 < 0; r0.g = (uint32_t)(r0.gneg ? -g0 : g0);
+        r1.fneg = f1 < 0; r1.f = (uint32_t)(r1.fneg ? -f1 : f1);
+        r1.gneg = g1 < 0; r1.g = (uint32_t)(r1.gneg ? -g1 : g1);
+        uint32_t na[8], nb8[8];
+        if (bg_combine(a, b, r0, na)) {  // a came out negative: negate the row
+            r0.fneg = !r0.fneg;
+            r0.gneg = !r0.gneg;
+        }
+        if (bg_combine(a, b, r1, nb8)) {
+            r1.fneg = !r1.fneg;
+            r1.gneg = !r1.gneg;
+        }
+        uint32_t nu[8], nv[8];
+        bg_combine_mod<P>(u, v, r0, nu);
+        bg_combine_mod<P>(u, v, r1, nv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            a[i] = na[i];
+            b[i] = nb8[i];
+            u[i] = nu[i];
+            v[i] = nv[i];
+        }
+    }
+    uint32_t rest = (b[0] ^ 1u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) rest |= b[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) rest |= a[i];
+    if (rest) return fp_inv_euclid(y);  // (not reached for a prime modulus: gcd = 1 within 2 * 254 steps)
+    Fp<P> x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x.l[i] = v[i];
+    const Fp<P> r3 = fp_mul(fp_r2<P>(), fp_r2<P>());
+    return fp_mul(x, r3);
 }
 
 }  // namespace kzg
