@@ -31,7 +31,7 @@ TAU_SEED = 1001
 SCALAR_SEED = 6
 PROVE_SEED = 4           # config C4
 MACS_PER_POINT_WINDOW = 10 * 136   # XYZZ mixed add = 8M + 2S = 10 modmul x 136 limb-MACs
-NCU_TRAFFIC_2_24 = 1.051e11            # DRAM bytes (read + write) of one bucket accumulation at 2^24 points: ncu, profiles/r01_msm24_launches.md
+NCU_TRAFFIC_2_24 = 7.974e10            # DRAM bytes (read + write) of one bucket accumulation at 2^24 points: ncu, profiles/r01_msm24_launches.md
 
 
 def parse_args():
