@@ -155,3 +155,40 @@ def test_whole_proofs_with_forced_rounds(kind, rounds, curve, tau, ptau_factory,
     finally:
         monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
     assert pr.proof_bytes(got) == pr.proof_bytes(want)
+
+
+@pytest.mark.parametrize("pattern", ["uniform", "skewed", "two_values"])
+def test_default_rounds_at_2_22_points_known_answer(curve, tau, pattern):
+    """2^22 points over the window table: the rounds are on by the library's own choice.  Uniform scalars, three
+    quarters of the scalars equal (one bucket with millions of entries: a pairwise tree over one run, then the
+    block-tier collapse of its partial sums) and scalars taking two values only.  Known answer (sum s_i tau^i) G1 with
+    the sum evaluated by the device Horner kernel (an independent path; bench.py's check)."""
+    import numpy as np
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200._lib import as_ptr
+    n = 1 << 22
+    srs = C.c_void_p()
+    curve.check(curve.lib.kzg_srs_generate(curve.ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
+    try:
+        curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, 0))
+        c, w, r = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        curve.check(curve.lib.kzg_msm_plan(curve.ctx, srs, n, 0, C.byref(c), C.byref(w), C.byref(r)))
+        assert r.value >= 1, "the batched-affine rounds should be on at 2^22 points"
+        scal = synthetic.random_fr_std(77, n).copy()
+        if pattern == "skewed":
+            scal[: 3 * n // 4] = np.array([5, 0, 0, 0], dtype=np.uint64)
+        elif pattern == "two_values":
+            scal[0::2] = np.array([(1 << 20) + 3, 0, 0, 0], dtype=np.uint64)
+            scal[1::2] = scal[1]
+        buf = curve.to_device(scal.tobytes())
+        out = bytearray(64)
+        curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out)))
+        # sum s_i tau^i: the standard-form scalars re-read as Montgomery residues have value s_i / 2^256, and the result
+        # comes back as Montgomery bytes, so the raw little-endian integer is the sum itself
+        ev = bytearray(32)
+        tau_m = (tau << 256) % R
+        curve.check(curve.lib.kzg_poly_evaluate(curve.ctx, buf.handle, as_ptr(tau_m.to_bytes(32, "little")), as_ptr(ev)))
+        k = int.from_bytes(ev, "little") % R
+        assert bytes(out) == bn.g1_to_bytes(bn.g1_mul_gen(k)), pattern
+    finally:
+        curve.lib.kzg_srs_free(curve.ctx, srs)
