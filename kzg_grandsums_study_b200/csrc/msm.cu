@@ -618,12 +618,25 @@ __device__ __forceinline__ G1XYZZ load_xyzz(const G1XYZZ* p) {
     return v;
 }
 
+__device__ __forceinline__ G1Affine load_dense_point(const Fq* xs, const Fq* ys, uint32_t i) {
+    G1Affine r;
+    const uint4* qx = reinterpret_cast<const uint4*>(xs + i);
+    const uint4* qy = reinterpret_cast<const uint4*>(ys + i);
+    uint4 a = __ldg(qx), b = __ldg(qx + 1), c = __ldg(qy), d = __ldg(qy + 1);
+    r.x.l[0] = a.x; r.x.l[1] = a.y; r.x.l[2] = a.z; r.x.l[3] = a.w;
+    r.x.l[4] = b.x; r.x.l[5] = b.y; r.x.l[6] = b.z; r.x.l[7] = b.w;
+    r.y.l[0] = c.x; r.y.l[1] = c.y; r.y.l[2] = c.z; r.y.l[3] = c.w;
+    r.y.l[4] = d.x; r.y.l[5] = d.y; r.y.l[6] = d.z; r.y.l[7] = d.w;
+    return r;
+}
+
 // One thread per slice of `slice` consecutive entries of the sorted list: equal work per lane no matter how
 // the bucket sizes fluctuate.  Whenever the walk crosses a bucket boundary the running sum is parked in the
 // partial-sum slot of (bucket, slice):  pbase[key] + (slice index - first slice of the bucket).
 // DIRECT: the list is a dense array of points in bucket order (what the batched-affine rounds below leave), not indices.
 template <bool DIRECT>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __restrict__ bases,
+                                                             const Fq* __restrict__ dense_x, const Fq* __restrict__ dense_y,
                                                              const uint32_t* __restrict__ sorted,
                                                              const uint32_t* __restrict__ offsets,
                                                              const uint32_t* __restrict__ pbase, uint32_t nkeys,
@@ -646,7 +659,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
 
     G1XYZZ acc = xyzz_inf();
     uint32_t e = DIRECT ? begin : sorted[begin];
-    G1Affine p = DIRECT ? load_affine(bases + e) : load_affine_gather(bases + (e & 0x7fffffffu));
+    G1Affine p = DIRECT ? load_dense_point(dense_x, dense_y, e) : load_affine_gather(bases + (e & 0x7fffffffu));
     for (uint32_t j = begin; j < end; j++) {
         if (j == key_end) {  // bucket boundary inside the slice
             store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
@@ -661,7 +674,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
         G1Affine p_next = p;
         if (j + 1 < end) {
             e_next = DIRECT ? j + 1 : sorted[j + 1];
-            p_next = DIRECT ? load_affine(bases + e_next) : load_affine_gather(bases + (e_next & 0x7fffffffu));
+            p_next = DIRECT ? load_dense_point(dense_x, dense_y, e_next) : load_affine_gather(bases + (e_next & 0x7fffffffu));
         }
         if (!DIRECT && (e >> 31)) p.y = fp_neg(p.y);
         xyzz_madd(acc, p);
@@ -693,7 +706,8 @@ constexpr int AFF_THREADS = 128;
 struct AffRound {
     const G1Affine* bases;    // round 1: window table / points, addressed through `sorted` (index | sign << 31)
     const uint32_t* sorted;   // round 1 only, nullptr afterwards
-    const G1Affine* in;       // later rounds: the dense list left by the previous round
+    const Fq* in_x;           // later rounds: the dense list left by the previous round, as two planes (all x, all y):
+    const Fq* in_y;           // the forward pass needs the x coordinates only and then streams half the bytes
     const uint32_t* off_in;   // bucket offsets of the input list  (nkeys + 1)
     const uint32_t* off_out;  // bucket offsets of the output list (nkeys + 1): scan of ceil(count / 2)
     uint32_t nkeys;
@@ -710,30 +724,21 @@ __device__ __forceinline__ Fq load_fq_ldg(const Fq* p) {
     return r;
 }
 // operand handles: position in the dense input list, or (round 1) the sorted entry itself: index | sign << 31
+// (the sign is applied by the consumer: a prefetch must not touch what it loads -- the first use of a loaded
+// register is where the warp waits)
 template <bool INDEXED>
-__device__ __forceinline__ const G1Affine* aff_operand(const AffRound& a, uint32_t h, uint32_t& neg) {
-    if (INDEXED) {
-        neg = h >> 31;
-        return a.bases + (h & 0x7fffffffu);
-    }
-    neg = 0;
-    return a.in + h;
+__device__ __forceinline__ G1Affine aff_request_point(const AffRound& a, uint32_t h) {
+    if (INDEXED) return load_affine_gather(a.bases + (h & 0x7fffffffu));
+    G1Affine p;
+    p.x = load_fq_ldg(a.in_x + h);
+    p.y = load_fq_ldg(a.in_y + h);
+    return p;
 }
 template <bool INDEXED>
 __device__ __forceinline__ G1Affine aff_load_point(const AffRound& a, uint32_t h) {
-    uint32_t neg;
-    const G1Affine* q = aff_operand<INDEXED>(a, h, neg);
-    G1Affine p = INDEXED ? load_affine_gather(q) : load_affine(q);
-    if (neg) p.y = fp_neg(p.y);
+    G1Affine p = aff_request_point<INDEXED>(a, h);
+    if (INDEXED && (h >> 31)) p.y = fp_neg(p.y);
     return p;
-}
-// the same without the sign: a prefetch must not touch what it loads (the first use of a loaded register is where
-// the warp waits), so the software pipeline of msm_aff_backward applies the sign when the point is consumed
-template <bool INDEXED>
-__device__ __forceinline__ G1Affine aff_request_point(const AffRound& a, uint32_t h) {
-    uint32_t neg;
-    const G1Affine* q = aff_operand<INDEXED>(a, h, neg);
-    return INDEXED ? load_affine_gather(q) : load_affine(q);
 }
 // both operands of output o's pair
 template <bool INDEXED>
@@ -813,9 +818,7 @@ __device__ __forceinline__ void aff_step_down(const AffRound& a, AffCursor& c, u
 
 template <bool INDEXED>
 __device__ __forceinline__ Fq aff_load_x(const AffRound& a, uint32_t h) {
-    uint32_t neg;
-    const Fq* x = &aff_operand<INDEXED>(a, h, neg)->x;
-    return INDEXED ? load_fq_gather(x) : load_fq_ldg(x);
+    return INDEXED ? load_fq_gather(&(a.bases + (h & 0x7fffffffu))->x) : load_fq_ldg(a.in_x + h);
 }
 
 template <bool INDEXED>
@@ -873,15 +876,10 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRoun
     fp_store(totals + t, acc);
 }
 
-__device__ __forceinline__ void store_affine(G1Affine* p, const G1Affine& v) {
-    fp_store(&p->x, v.x);
-    fp_store(&p->y, v.y);
-}
-
 template <bool INDEXED>
 __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRound a, uint32_t m, const Fq* __restrict__ prefix,
                                                                           const Fq* __restrict__ inv_totals,
-                                                                          G1Affine* __restrict__ out) {
+                                                                          Fq* __restrict__ out_x, Fq* __restrict__ out_y) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nthreads) return;
     const uint32_t total = a.off_out[a.nkeys];
@@ -948,7 +946,8 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRou
                 r.y = fp_zero<FqP>();
             }
         }
-        store_affine(out + o, r);
+        fp_store(out_x + o, r.x);
+        fp_store(out_y + o, r.y);
         if (!more) break;
         p1 = n1;
         p2 = n2;
@@ -1608,18 +1607,20 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
 
     // batched-affine rounds: (sorted, offsets) -> dense point lists, half as long each time
     const uint32_t* walk_offsets = offsets;
-    const G1Affine* walk_points = pts;
+    const Fq *walk_x = nullptr, *walk_y = nullptr;  // the dense list the rounds leave: a plane of x and a plane of y
     if (aff_rounds) timed_begin(ctx, KZG_TIMED_MSM_AFFINE);
     for (uint32_t r = 1; r <= aff_rounds; r++) {
         uint32_t* off_out = (uint32_t*)(sc + o_aff_off[r & 1]);
-        G1Affine* pts_out = (G1Affine*)(sc + o_aff_pts[(r & 1) ^ 1]);
+        Fq* out_x = (Fq*)(sc + o_aff_pts[(r & 1) ^ 1]);
+        Fq* out_y = out_x + aff_entries[(r & 1) ? 1 : 2];  // (capacity of that buffer in points)
         Fq* prefix = (Fq*)(sc + o_aff_prefix);
         Fq* totals = (Fq*)(sc + o_aff_totals);
         scan_offsets(r, off_out, cursor);  // (the scatter is done with `cursor`: free scratch)
         AffRound ar;
         ar.bases = pts;
         ar.sorted = r == 1 ? sorted : nullptr;
-        ar.in = r == 1 ? nullptr : walk_points;
+        ar.in_x = walk_x;
+        ar.in_y = walk_y;
         ar.off_in = walk_offsets;
         ar.off_out = off_out;
         ar.nkeys = nkeys;
@@ -1631,11 +1632,12 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
             KZG_LAUNCH(ctx, msm_aff_forward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals);
         KZG_TRY(fq_batch_inverse(ctx, totals, totals, ar.nthreads));
         if (r == 1)
-            KZG_LAUNCH(ctx, msm_aff_backward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals, pts_out);
+            KZG_LAUNCH(ctx, msm_aff_backward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals, out_x, out_y);
         else
-            KZG_LAUNCH(ctx, msm_aff_backward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals, pts_out);
+            KZG_LAUNCH(ctx, msm_aff_backward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals, out_x, out_y);
         walk_offsets = off_out;
-        walk_points = pts_out;
+        walk_x = out_x;
+        walk_y = out_y;
     }
     if (aff_rounds) timed_end(ctx, KZG_TIMED_MSM_AFFINE);
 
@@ -1647,10 +1649,12 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const uint32_t ablocks = (uint32_t)((max_tasks + 127) / 128);
     timed_begin(ctx, KZG_TIMED_MSM_ACCUMULATE);
     if (aff_rounds)
-        KZG_LAUNCH(ctx, msm_accumulate_kernel<true>, ablocks, 128, 0, walk_points, (const uint32_t*)nullptr, walk_offsets, segoff,
+        KZG_LAUNCH(ctx, msm_accumulate_kernel<true>, ablocks, 128, 0, (const G1Affine*)nullptr, walk_x, walk_y,
+                   (const uint32_t*)nullptr, walk_offsets, segoff,
                    nkeys, g.seg, partials);
     else
-        KZG_LAUNCH(ctx, msm_accumulate_kernel<false>, ablocks, 128, 0, pts, sorted, offsets, segoff, nkeys, g.seg, partials);
+        KZG_LAUNCH(ctx, msm_accumulate_kernel<false>, ablocks, 128, 0, pts, (const Fq*)nullptr, (const Fq*)nullptr, sorted, offsets,
+                   segoff, nkeys, g.seg, partials);
     timed_end(ctx, KZG_TIMED_MSM_ACCUMULATE);
     timed_begin(ctx, KZG_TIMED_MSM_REDUCE);
     KZG_LAUNCH(ctx, msm_collapse_huge_kernel, 128, 512, 0, partials, segoff, huge + 1, huge);
