@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
 //                     exclusive prefix products -> prefix[j][t], thread product -> totals[t]
 //   fq_batch_inverse  totals <- 1 / totals   (frops.cu, ~4.3 / AFF_M modmul per addition)
 //   msm_aff_backward  walks its outputs backwards peeling 1 / d_j off the inverse (2 modmul), finishes the additions,
-//                     writes the 64-byte affine results
+//                     writes the affine results as two planes (all x, all y: the next forward pass reads x only)
 // Exceptional pairs are decided from the operands alone, identically in both kernels: an operand at infinity, P + P
 // (tangent: d = 2 y, numerator 3 x^2), P + (-P) = infinity; they put d = 1 into the batch where no quotient is needed.
 // ---------------------------------------------------------------------------------------------
