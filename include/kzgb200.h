@@ -49,6 +49,16 @@ enum { KZG_GRANDSUM = 0, KZG_GRANDPRODUCT = 1 };
 int kzg_ctx_create(int device, void* stream, kzg_ctx** out);
 int kzg_ctx_destroy(kzg_ctx* ctx);
 int kzg_ctx_sync(kzg_ctx* ctx);
+/* Stream ordering against a caller-owned stream without a host synchronisation: the context's stream waits for what is
+ * queued on `stream` / `stream` waits for what is queued on the context's stream.  (The multi-rank MSM exchanges its
+ * partial points with a collective on the caller's stream.) */
+int kzg_ctx_wait_stream(kzg_ctx* ctx, void* stream);
+int kzg_stream_wait_ctx(kzg_ctx* ctx, void* stream);
+/* Tuning knobs of the MSM (A/B timing, forced paths in tests; none changes a result).  The KZGB200_<NAME> environment
+ * variables are read once at kzg_ctx_create; value < 0 restores the default.  Names: aff_rounds, aff_m, aff_chunks,
+ * aff_min_entries_log, aff_min_left_log, aff_min_fill, part_sort, red_k0, tail_width, host_piece_min_log,
+ * split_min_log, split_max_log, msm_merge. */
+int kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value);
 const char* kzg_last_error(kzg_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t kzg_ctx_launch_count(kzg_ctx* ctx);
@@ -148,9 +158,15 @@ int kzg_srs_msm(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std
  * partials, kzg_g1_partials_combine adds `count` of them and returns the affine point. */
 int kzg_srs_msm_partial(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std, uint64_t n, void* partial_dev);
 int kzg_g1_partials_combine(kzg_ctx* ctx, const void* partials_dev, uint32_t count, uint8_t out_affine[64]);
-/* Same, scalars in HOST memory (H2D inside the call): the end-to-end form of kzg_srs_msm. */
+/* Same, scalars in HOST memory (H2D inside the call): the end-to-end form of kzg_srs_msm / kzg_srs_msm_partial. */
 int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
                      uint8_t out_affine[64]);
+int kzg_srs_msm_host_partial(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
+                             void* partial_dev);
+/* commit(pol) for `count` polynomials over one SRS as ONE pipeline (multi-MSM over shared bases; the
+ * reference's separate commits of one round: prover.js:161-162 [F],[T]; :409-410 [Wxi],[Wxiw]): one sort, one bucket
+ * accumulation, one reduction with a bucket set per polynomial.  out_affine: 64 B per polynomial, in order. */
+int kzg_commit_many(kzg_ctx* ctx, kzg_srs* srs, kzg_buf* const* coefs, uint32_t count, uint8_t* out_affine);
 /* One-off per resident SRS: the window table T[w][i] = 2^(c w) [tau^i]_1 that lets every MSM over this SRS use a
  * single shared bucket set (fewer, larger windows; no doubling chain).  window_bits = 0 picks c from the SRS size.
  * Costs ceil(257/c) x the SRS memory.  Without it the SRS entry points fall back to the per-window MSM. */

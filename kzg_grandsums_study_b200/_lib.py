@@ -21,6 +21,9 @@ SIGNATURES = {
     "kzg_ctx_create": (i32, [i32, vp, C.POINTER(vp)]),
     "kzg_ctx_destroy": (i32, [vp]),
     "kzg_ctx_sync": (i32, [vp]),
+    "kzg_ctx_wait_stream": (i32, [vp, vp]),
+    "kzg_stream_wait_ctx": (i32, [vp, vp]),
+    "kzg_ctx_set_option": (i32, [vp, C.c_char_p, C.c_int64]),
     "kzg_last_error": (C.c_char_p, [vp]),
     "kzg_ctx_launch_count": (u64, [vp]),
     "kzg_selftest": (i32, [vp, u32]),
@@ -72,6 +75,8 @@ SIGNATURES = {
     "kzg_srs_msm_partial": (i32, [vp, vp, u64, vp, u64, vp]),
     "kzg_g1_partials_combine": (i32, [vp, vp, u32, vp]),
     "kzg_srs_msm_host": (i32, [vp, vp, u64, vp, u64, vp]),
+    "kzg_srs_msm_host_partial": (i32, [vp, vp, u64, vp, u64, vp]),
+    "kzg_commit_many": (i32, [vp, vp, C.POINTER(vp), u32, vp]),
     "kzg_srs_precompute": (i32, [vp, vp, u32]),
     "kzg_msm_geometry": (i32, [vp, vp, u64, i32, C.POINTER(u32), C.POINTER(u32)]),
     "kzg_msm_plan": (i32, [vp, vp, u64, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),

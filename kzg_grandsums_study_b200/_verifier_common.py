@@ -44,6 +44,8 @@ def verify(kind, pTauFilename, proof, nBits, logger=None):
     for nm in names:
         if nm not in Cm or len(Cm[nm]) != 64:
             return err("missing commitment %s" % nm)
+        if not hb.g1_bytes_canonical(Cm[nm]):
+            return err("%s is not a canonically encoded G1 element" % nm)
         P = hb.g1_from_bytes(Cm[nm])
         if not hb.g1_is_valid(P):
             return err("%s is not a valid G1 element" % nm)
@@ -60,6 +62,12 @@ def verify(kind, pTauFilename, proof, nBits, logger=None):
     for nm in ev_names:
         if nm not in Ev or int.from_bytes(bytes(Ev[nm]), "little") >= R:
             return err("%s is not a valid field element" % nm)
+    if isSelected:
+        # (not range-checked by the reference, but they must be there: a selected proof without them is malformed, not
+        # a crash)
+        for nm in ("selFxi", "selTxi"):
+            if nm not in Ev or len(bytes(Ev[nm])) != 32:
+                return err("missing evaluation %s" % nm)
     val = {k: Fr.toObject(v) for k, v in Ev.items()}
 
     # ---- STEP 3: challenges (:246-312)

@@ -124,15 +124,18 @@ static int build_common(kzg_ctx* ctx, int kind, kzg_buf* ev_f, kzg_buf* ev_t, kz
 
 int kzg_grandsum_build(kzg_ctx* ctx, kzg_buf* ev_f, kzg_buf* ev_t, kzg_buf* sel_f, kzg_buf* sel_t, const uint8_t gamma[32],
                        kzg_buf** s_coef) {
+    kzg::DeviceGuard _dg(ctx);
     return build_common(ctx, KZG_GRANDSUM, ev_f, ev_t, sel_f, sel_t, gamma, s_coef);
 }
 int kzg_grandproduct_build(kzg_ctx* ctx, kzg_buf* ev_f, kzg_buf* ev_t, kzg_buf* sel_f, kzg_buf* sel_t,
                            const uint8_t gamma[32], kzg_buf** z_coef) {
+    kzg::DeviceGuard _dg(ctx);
     return build_common(ctx, KZG_GRANDPRODUCT, ev_f, ev_t, sel_f, sel_t, gamma, z_coef);
 }
 
 // p(X) -> p(wX), w = Fr.w[log2 len]: coefficient i times w^i (what fft / rotate / ifft computes)
 int kzg_poly_shift_omega(kzg_ctx* ctx, kzg_buf* a, kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !a || !out) return KZG_ERR_ARG;
     const uint64_t n = a->n;
     if (n == 0 || (n & (n - 1))) return set_err(ctx, KZG_ERR_PROTOCOL, "fft must be multiple of 2");
@@ -150,6 +153,7 @@ int kzg_poly_shift_omega(kzg_ctx* ctx, kzg_buf* a, kzg_buf** out) {
 }
 
 int kzg_poly_div_zh(kzg_ctx* ctx, kzg_buf* a, uint64_t domain_size, kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !a || !out || domain_size == 0) return KZG_ERR_ARG;
     if (a->n % domain_size) return set_err(ctx, KZG_ERR_ARG, "divZh: length must be a multiple of the domain size");
     const uint64_t n = domain_size;

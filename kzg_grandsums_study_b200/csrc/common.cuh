@@ -9,8 +9,34 @@
 #include "../../include/kzgb200.h"
 #include "ec.cuh"
 
+// MSM tuning knobs.  Defaults are the measured optima; the KZGB200_* environment variables of the same names are read
+// ONCE, when the context is created, and kzg_ctx_set_option changes them afterwards (A/B timing, the forced paths of
+// tests/).  None of them changes a result -- every path ends in the same canonical affine point.
+struct MsmTuning {
+    int aff_rounds = -1;            // batched-affine rounds before the XYZZ walk; -1: the cost rule of msm_affine_rounds
+    uint32_t aff_m = 16;            // output points per thread of a round
+    int aff_chunks = 0;             // chunks a round is launched in (inversion hidden under the other chunks); 0: auto
+    uint64_t aff_min_entries = 20ull << 20;  // no rounds below this many bucket entries
+    uint64_t aff_min_left = 1ull << 22;      // a round must leave at least this many points
+    double aff_min_fill = 6.0;      // ... and find at least this many entries per bucket
+    int part_sort = -1;             // 0 / 1: direct counting sort / two-level partition sort; -1: by size
+    int red_k0 = -1;                // log2 of the level-0 radix of the bucket reduction; -1: by size
+    int tail_width = 0;             // threads per tail task (32 / 64 / 128); 0: by size
+    int host_cut_a = 0, host_cut_b = 64;  // host-scalar MSM: piece cuts at a/64 and b/64 of the points; 0: default
+    uint32_t host_piece_min_log = 22;     // ... pieces from 2^this points on
+    int split_min_log = -1, split_max_log = -1;  // two-lane split of ONE msm (off: measured slower since the affine rounds)
+    int merge = 1;                  // commitments of one round over one table as one merged pipeline
+    int timeline = 0;               // debug: print where the time of every affine round goes (events on all three streams)
+};
+
 struct kzg_ctx {
     int device = 0;
+    MsmTuning tuning;
+    cudaStream_t inv_stream[2] = {nullptr, nullptr};  // high priority, one per lane: the inversions of the affine rounds
+    cudaStream_t side_stream[2] = {nullptr, nullptr}; // one per lane: every other chunk of an affine round (tails overlap)
+    std::vector<cudaEvent_t> order_events;            // ring of ordering events (msm.cu order_event)
+    size_t order_next = 0;
+    std::vector<std::pair<cudaEvent_t, std::string>> timeline;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
@@ -37,6 +63,7 @@ struct kzg_ctx {
     cudaStream_t aux_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // host-scalar MSMs: the piecewise upload, so that both lanes can compute under it
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_order = nullptr;  // kzg_ctx_wait_stream / kzg_stream_wait_ctx
     int lane = 0;
     bool no_split = false;  // KZGB200_NO_SPLIT=1: mid-sized MSMs are not split over the two lanes (A/B timing)
     // persistent scratch per lane (grown on demand)
@@ -74,6 +101,24 @@ constexpr uint32_t TW_SIZE = 1u << TW_BITS;
 constexpr uint32_t NTT_MAX_LOG = 2 * TW_BITS;  // 26
 
 int set_err(kzg_ctx* ctx, int code, const std::string& msg);
+
+// Every extern "C" entry point that takes a context (or an object that owns one) starts with this guard: the calling
+// thread's current CUDA device becomes the context's for the duration of the call and is restored afterwards, so that
+// several contexts on different GPUs can be driven from one process (the multi-GPU MSM of mgpu.cu, getCurveFromName(name,
+// device) in the host layer).  Allocation, kernel launches and stream operations all go to the current device.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(const kzg_ctx* c) {
+        if (!c) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != c->device) changed = cudaSetDevice(c->device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 #define KZG_CUDA(ctx, expr)                                                                   \
     do {                                                                                      \
@@ -134,6 +179,7 @@ struct MsmJob {
     uint64_t n;
 };
 int msm_run_batch(kzg_ctx* ctx, const MsmJob* jobs, uint32_t count, uint8_t* out_affine);
+int ctx_set_option(kzg_ctx* ctx, const char* name, long long value);
 // frops.cu
 int fr_convert(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n, bool to_mont);
 int fr_batch_inverse(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n);

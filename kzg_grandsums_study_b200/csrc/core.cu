@@ -1,4 +1,5 @@
 // Context, device buffers and the bulk-Fr / Polynomial C ABI of libkzgb200.so.
+#include <ctype.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -9,6 +10,29 @@ namespace kzg {
 int set_err(kzg_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     return code;
+}
+
+int ctx_set_option(kzg_ctx* ctx, const char* name, long long value) {
+    MsmTuning& t = ctx->tuning;
+    const MsmTuning def;
+    const std::string k = name ? name : "";
+    const bool reset = value < 0;
+    if (k == "aff_rounds") t.aff_rounds = reset ? def.aff_rounds : (int)value;
+    else if (k == "aff_m") t.aff_m = reset || value == 0 ? def.aff_m : (uint32_t)(value > 256 ? 256 : value);
+    else if (k == "aff_chunks") t.aff_chunks = reset ? def.aff_chunks : (int)value;
+    else if (k == "aff_min_entries_log") t.aff_min_entries = reset ? def.aff_min_entries : 1ull << (value > 40 ? 40 : value);
+    else if (k == "aff_min_left_log") t.aff_min_left = reset ? def.aff_min_left : 1ull << (value > 40 ? 40 : value);
+    else if (k == "aff_min_fill") t.aff_min_fill = reset ? def.aff_min_fill : (double)value;
+    else if (k == "part_sort") t.part_sort = reset ? def.part_sort : (int)value;
+    else if (k == "red_k0") t.red_k0 = reset ? def.red_k0 : (int)value;
+    else if (k == "tail_width") t.tail_width = reset ? def.tail_width : (int)value;
+    else if (k == "host_piece_min_log") t.host_piece_min_log = reset ? def.host_piece_min_log : (uint32_t)value;
+    else if (k == "split_min_log") t.split_min_log = reset ? def.split_min_log : (int)value;
+    else if (k == "split_max_log") t.split_max_log = reset ? def.split_max_log : (int)value;
+    else if (k == "msm_merge") t.merge = reset ? def.merge : (int)value;
+    else if (k == "timeline") t.timeline = reset ? 0 : (int)value;
+    else return set_err(ctx, KZG_ERR_ARG, "unknown option: " + k);
+    return KZG_OK;
 }
 
 static cudaEvent_t take_event(kzg_ctx* ctx) {
@@ -238,11 +262,38 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return KZG_ERR_CUDA;
     }
+    {
+        int lo = 0, hi = 0;  // (numerically lowest = greatest priority)
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int l = 0; l < 2; l++)
+            if (cudaStreamCreateWithPriority(&ctx->inv_stream[l], cudaStreamNonBlocking, hi) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&ctx->side_stream[l], cudaStreamNonBlocking) != cudaSuccess) {
+                delete ctx;
+                return KZG_ERR_CUDA;
+            }
+    }
     ctx->no_split = getenv("KZGB200_NO_SPLIT") != nullptr;
+    // the tuning knobs, read once (kzg_ctx_set_option changes them later)
+    static const char* const knobs[] = {"aff_rounds", "aff_m", "aff_chunks", "aff_min_entries_log", "aff_min_left_log",
+                                        "aff_min_fill", "part_sort", "red_k0", "tail_width", "host_piece_min_log",
+                                        "split_min_log", "split_max_log", "msm_merge", "timeline"};
+    for (const char* k : knobs) {
+        std::string env = "KZGB200_";
+        for (const char* c = k; *c; c++) env += (char)toupper(*c);
+        if (const char* ov = getenv(env.c_str())) ctx_set_option(ctx, k, atoll(ov));
+    }
+    if (const char* ov = getenv("KZGB200_HOST_PIECES")) {  // "a,b" = cuts at a/64 and b/64 of n (b = 64: two pieces)
+        int a = 0, b = 64;
+        if (sscanf(ov, "%d,%d", &a, &b) >= 1 && a > 0 && a < b && b <= 64) {
+            ctx->tuning.host_cut_a = a;
+            ctx->tuning.host_cut_b = b;
+        }
+    }
     if (const char* ov = getenv("KZGB200_L2_FETCH")) {  // experiment: bytes the L2 fetches from DRAM per miss
         size_t before = 0, after = 0;
         cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
@@ -277,6 +328,7 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
 }
 
 int kzg_ctx_destroy(kzg_ctx* ctx) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx) return KZG_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -303,6 +355,18 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
+    for (int l = 0; l < 2; l++) {
+        if (ctx->inv_stream[l]) {
+            cudaStreamSynchronize(ctx->inv_stream[l]);
+            cudaStreamDestroy(ctx->inv_stream[l]);
+        }
+        if (ctx->side_stream[l]) {
+            cudaStreamSynchronize(ctx->side_stream[l]);
+            cudaStreamDestroy(ctx->side_stream[l]);
+        }
+    }
+    for (cudaEvent_t e : ctx->order_events) cudaEventDestroy(e);
     cudaFree(ctx->dev_small);
     cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -311,13 +375,45 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
 }
 
 int kzg_ctx_sync(kzg_ctx* ctx) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx) return KZG_ERR_ARG;
     KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KZG_OK;
 }
 
-const char* kzg_last_error(kzg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-uint64_t kzg_ctx_launch_count(kzg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int kzg_ctx_set_option(kzg_ctx* ctx, const char* name, int64_t value) {
+    kzg::DeviceGuard _dg(ctx);
+    if (!ctx || !name) return KZG_ERR_ARG;
+    return ctx_set_option(ctx, name, (long long)value);
+}
+
+// stream ordering against a caller-owned stream (the multi-GPU MSM exchanges the partial points with a collective
+// that runs on the caller's stream): no host synchronisation, one event each way
+int kzg_ctx_wait_stream(kzg_ctx* ctx, void* stream) {
+    kzg::DeviceGuard _dg(ctx);
+    if (!ctx) return KZG_ERR_ARG;
+    if ((cudaStream_t)stream == ctx->stream) return KZG_OK;
+    KZG_CUDA(ctx, cudaEventRecord(ctx->ev_order, (cudaStream_t)stream));
+    KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_order, 0));
+    return KZG_OK;
+}
+int kzg_stream_wait_ctx(kzg_ctx* ctx, void* stream) {
+    kzg::DeviceGuard _dg(ctx);
+    if (!ctx) return KZG_ERR_ARG;
+    if ((cudaStream_t)stream == ctx->stream) return KZG_OK;
+    KZG_CUDA(ctx, cudaEventRecord(ctx->ev_order, ctx->stream));
+    KZG_CUDA(ctx, cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_order, 0));
+    return KZG_OK;
+}
+
+const char* kzg_last_error(kzg_ctx* ctx) {
+    kzg::DeviceGuard _dg(ctx);
+    return ctx ? ctx->err.c_str() : "null context";
+}
+uint64_t kzg_ctx_launch_count(kzg_ctx* ctx) {
+    kzg::DeviceGuard _dg(ctx);
+    return ctx ? ctx->launches : 0;
+}
 
 // quad-lane group law (ec.cuh) against the scalar formulas: generic sums, doublings through the addition,
 // cancellation, infinities, small multiples.  One case per quad.
@@ -358,6 +454,7 @@ __global__ void selftest_quad_kernel(uint32_t n, unsigned int* fail) {
 }
 
 int kzg_selftest(kzg_ctx* ctx, uint32_t n_cases) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx) return KZG_ERR_ARG;
     unsigned int* slot = (unsigned int*)ctx->dev_small;
     KZG_CUDA(ctx, cudaMemsetAsync(slot, 0, sizeof(unsigned int), ctx->stream));
@@ -411,15 +508,18 @@ static int bench_peak(kzg_ctx* ctx, int which, uint32_t ms, double* macs_per_sec
 }
 
 int kzg_bench_imad_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !macs_per_second) return KZG_ERR_ARG;
     return bench_peak(ctx, 0, ms, macs_per_second);
 }
 int kzg_bench_modmul_peak(kzg_ctx* ctx, uint32_t ms, double* macs_per_second) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !macs_per_second) return KZG_ERR_ARG;
     return bench_peak(ctx, 1, ms, macs_per_second);
 }
 
 int kzg_ctx_kernel_time(kzg_ctx* ctx, uint32_t which, int reset, double* ms_out, uint64_t* launches_out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || which >= KZG_TIMED_TAGS) return KZG_ERR_ARG;
     KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double total = 0;
@@ -444,10 +544,12 @@ int kzg_ctx_kernel_time(kzg_ctx* ctx, uint32_t which, int reset, double* ms_out,
 
 // ---- buffers ------------------------------------------------------------------------------------
 int kzg_buf_alloc(kzg_ctx* ctx, uint64_t n, kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !out) return KZG_ERR_ARG;
     return buf_new(ctx, n, true, out);
 }
 int kzg_buf_free(kzg_ctx* ctx, kzg_buf* b) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !b) return KZG_OK;
     if (b->d) cudaFreeAsync(b->d, ctx->stream);
     delete b;
@@ -457,6 +559,7 @@ uint64_t kzg_buf_len(kzg_buf* b) { return b ? b->n : 0; }
 void* kzg_buf_device_ptr(kzg_buf* b) { return b ? (void*)b->d : nullptr; }
 
 int kzg_buf_upload(kzg_ctx* ctx, kzg_buf* dst, uint64_t dst_off, const uint8_t* host, uint64_t n) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !dst || (!host && n)) return KZG_ERR_ARG;
     if (dst_off + n > dst->n) return set_err(ctx, KZG_ERR_ARG, "upload out of bounds");
     if (n == 0) return KZG_OK;
@@ -465,6 +568,7 @@ int kzg_buf_upload(kzg_ctx* ctx, kzg_buf* dst, uint64_t dst_off, const uint8_t* 
     return KZG_OK;
 }
 int kzg_buf_download(kzg_ctx* ctx, kzg_buf* src, uint64_t src_off, uint8_t* host, uint64_t n) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !src || (!host && n)) return KZG_ERR_ARG;
     if (src_off + n > src->n) return set_err(ctx, KZG_ERR_ARG, "download out of bounds");
     if (n == 0) return KZG_OK;
@@ -473,6 +577,7 @@ int kzg_buf_download(kzg_ctx* ctx, kzg_buf* src, uint64_t src_off, uint8_t* host
     return KZG_OK;
 }
 int kzg_buf_copy(kzg_ctx* ctx, kzg_buf* dst, uint64_t dst_off, kzg_buf* src, uint64_t src_off, uint64_t n) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !dst || !src) return KZG_ERR_ARG;
     if (dst_off + n > dst->n || src_off + n > src->n) return set_err(ctx, KZG_ERR_ARG, "copy out of bounds");
     if (n == 0) return KZG_OK;
@@ -480,6 +585,7 @@ int kzg_buf_copy(kzg_ctx* ctx, kzg_buf* dst, uint64_t dst_off, kzg_buf* src, uin
     return KZG_OK;
 }
 int kzg_buf_fill(kzg_ctx* ctx, kzg_buf* dst, uint64_t off, uint64_t n, const uint8_t value[32]) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !dst || !value) return KZG_ERR_ARG;
     if (off + n > dst->n) return set_err(ctx, KZG_ERR_ARG, "fill out of bounds");
     return fr_fill(ctx, dst->d + off, n, fr_from_bytes(value));
@@ -487,10 +593,12 @@ int kzg_buf_fill(kzg_ctx* ctx, kzg_buf* dst, uint64_t off, uint64_t n, const uin
 
 // ---- bulk Fr ------------------------------------------------------------------------------------
 int kzg_fr_to_mont(kzg_ctx* ctx, kzg_buf* in, kzg_buf* out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !in || !out || in->n != out->n) return KZG_ERR_ARG;
     return fr_convert(ctx, in->d, out->d, in->n, true);
 }
 int kzg_fr_from_mont(kzg_ctx* ctx, kzg_buf* in, kzg_buf* out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !in || !out || in->n != out->n) return KZG_ERR_ARG;
     return fr_convert(ctx, in->d, out->d, in->n, false);
 }
@@ -501,12 +609,14 @@ static int log2_exact(uint64_t n) {
     return l;
 }
 int kzg_fr_ntt(kzg_ctx* ctx, kzg_buf* in, kzg_buf* out, int inverse) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !in || !out || in->n != out->n) return KZG_ERR_ARG;
     int lg = log2_exact(in->n);
     if (lg < 0) return set_err(ctx, KZG_ERR_PROTOCOL, "fft must be multiple of 2");
     return ntt_run(ctx, in->d, in->n, out->d, (uint32_t)lg, inverse != 0);
 }
 int kzg_fr_extend_ntt(kzg_ctx* ctx, kzg_buf* coef, uint32_t extension, kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !coef || !out || extension == 0 || (extension & (extension - 1))) return KZG_ERR_ARG;
     uint32_t power = 0;
     while ((1ull << power) < coef->n) power++;
@@ -523,6 +633,7 @@ int kzg_fr_extend_ntt(kzg_ctx* ctx, kzg_buf* coef, uint32_t extension, kzg_buf**
     return KZG_OK;
 }
 int kzg_fr_batch_inverse(kzg_ctx* ctx, kzg_buf* in, kzg_buf* out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !in || !out || in->n != out->n) return KZG_ERR_ARG;
     return fr_batch_inverse(ctx, in->d, out->d, in->n);
 }
@@ -544,10 +655,17 @@ static int poly_addsub(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out, bool
     *out = o;
     return KZG_OK;
 }
-int kzg_poly_add(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) { return poly_addsub(ctx, a, b, out, false); }
-int kzg_poly_sub(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) { return poly_addsub(ctx, a, b, out, true); }
+int kzg_poly_add(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
+    return poly_addsub(ctx, a, b, out, false);
+}
+int kzg_poly_sub(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
+    return poly_addsub(ctx, a, b, out, true);
+}
 
 int kzg_poly_mul_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32]) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !a || !s) return KZG_ERR_ARG;
     const Fr* polys[1] = {a->d};
     uint64_t lens[1] = {a->n};
@@ -564,14 +682,22 @@ static int poly_addsub_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32], boo
     if (sub) c = fp_neg(c);
     return poly_linear_combination(ctx, a->d, 1, polys, lens, coeffs, 1, c);
 }
-int kzg_poly_add_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32]) { return poly_addsub_scalar(ctx, a, s, false); }
-int kzg_poly_sub_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32]) { return poly_addsub_scalar(ctx, a, s, true); }
+int kzg_poly_add_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32]) {
+    kzg::DeviceGuard _dg(ctx);
+    return poly_addsub_scalar(ctx, a, s, false);
+}
+int kzg_poly_sub_scalar(kzg_ctx* ctx, kzg_buf* a, const uint8_t s[32]) {
+    kzg::DeviceGuard _dg(ctx);
+    return poly_addsub_scalar(ctx, a, s, true);
+}
 
 int kzg_poly_degree(kzg_ctx* ctx, kzg_buf* a, uint64_t* degree) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !a || !degree) return KZG_ERR_ARG;
     return poly_degree(ctx, a->d, a->n, degree);
 }
 int kzg_poly_evaluate(kzg_ctx* ctx, kzg_buf* a, const uint8_t x[32], uint8_t out[32]) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !a || !x || !out) return KZG_ERR_ARG;
     const Fr* polys[1] = {a->d};
     uint64_t lens[1] = {a->n};
@@ -582,6 +708,7 @@ int kzg_poly_evaluate(kzg_ctx* ctx, kzg_buf* a, const uint8_t x[32], uint8_t out
     return KZG_OK;
 }
 int kzg_poly_multiply(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !a || !b || !out) return KZG_ERR_ARG;
     uint64_t da = 0, db = 0;
     KZG_TRY(poly_degree(ctx, a->d, a->n, &da));
@@ -605,6 +732,7 @@ int kzg_poly_multiply(kzg_ctx* ctx, kzg_buf* a, kzg_buf* b, kzg_buf** out) {
     return KZG_OK;
 }
 int kzg_poly_lagrange1(kzg_ctx* ctx, uint32_t power, kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !out || power > 26) return KZG_ERR_ARG;
     // iNTT of e_0: every coefficient equals n^-1
     Fr n = fp_zero<FrP>();
@@ -623,6 +751,7 @@ int kzg_poly_lagrange1(kzg_ctx* ctx, uint32_t power, kzg_buf** out) {
     return KZG_OK;
 }
 int kzg_poly_div_x_sub_value(kzg_ctx* ctx, kzg_buf* a, const uint8_t v[32], kzg_buf** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !a || !v || !out) return KZG_ERR_ARG;
     if (a->n < 2) return set_err(ctx, KZG_ERR_ARG, "divByXSubValue needs at least two coefficients");
     kzg_buf* o = nullptr;

@@ -80,9 +80,8 @@ __global__ void __launch_bounds__(EW_THREADS) lincomb_kernel(Fr* __restrict__ ou
     }
     fp_store(out + i, acc);
 }
-int poly_linear_combination(kzg_ctx* ctx, Fr* out, uint64_t n_out, const Fr* const* polys, const uint64_t* lens,
-                            const Fr* coeffs, uint32_t count, const Fr& constant) {
-    if (count > LC_MAX) return set_err(ctx, KZG_ERR_ARG, "linear combination of more than 28 polynomials");
+static int lincomb_launch(kzg_ctx* ctx, Fr* out, uint64_t n_out, const Fr* const* polys, const uint64_t* lens,
+                          const Fr* coeffs, uint32_t count, const Fr& constant) {
     LinCombArgs a;
     memset(&a, 0, sizeof(a));
     for (uint32_t j = 0; j < count; j++) {
@@ -94,6 +93,33 @@ int poly_linear_combination(kzg_ctx* ctx, Fr* out, uint64_t n_out, const Fr* con
     a.count = count;
     KZG_LAUNCH(ctx, lincomb_kernel, grid_for(n_out, EW_THREADS), EW_THREADS, 0, out, n_out, a);
     KZG_CHECK_LAUNCH(ctx);
+    return KZG_OK;
+}
+// Any number of terms: the kernel takes LC_MAX per launch, further launches add LC_MAX - 1 more to the running result
+// (the reference accepts any number of columns, prover.js:34-45).  `out` may alias one of the inputs only when a single
+// launch suffices (element i is read before it is written by the same thread).
+int poly_linear_combination(kzg_ctx* ctx, Fr* out, uint64_t n_out, const Fr* const* polys, const uint64_t* lens,
+                            const Fr* coeffs, uint32_t count, const Fr& constant) {
+    if (count <= LC_MAX) return lincomb_launch(ctx, out, n_out, polys, lens, coeffs, count, constant);
+    for (uint32_t j = 0; j < count; j++)
+        if (polys[j] == out) return set_err(ctx, KZG_ERR_ARG, "linear combination: in-place use with more than 28 terms");
+    KZG_TRY(lincomb_launch(ctx, out, n_out, polys, lens, coeffs, LC_MAX, constant));
+    for (uint32_t done = LC_MAX; done < count;) {
+        const uint32_t take = count - done < LC_MAX - 1 ? count - done : LC_MAX - 1;
+        const Fr* ps[LC_MAX];
+        uint64_t ls[LC_MAX];
+        Fr cs[LC_MAX];
+        ps[0] = out;
+        ls[0] = n_out;
+        cs[0] = fp_one<FrP>();
+        for (uint32_t j = 0; j < take; j++) {
+            ps[1 + j] = polys[done + j];
+            ls[1 + j] = lens[done + j];
+            cs[1 + j] = coeffs[done + j];
+        }
+        KZG_TRY(lincomb_launch(ctx, out, n_out, ps, ls, cs, take + 1, fp_zero<FrP>()));
+        done += take;
+    }
     return KZG_OK;
 }
 

@@ -45,9 +45,21 @@ struct MsmGeom {
     uint32_t c;         // window bits
     uint32_t nwin;      // digits per scalar
     uint32_t nbuckets;  // buckets per set = 2^(c-1)
-    uint32_t nsets;     // bucket sets: 1 with a precomputed table, nwin without
+    uint32_t nsets;     // bucket sets: one per job with a precomputed table, nwin without
+    uint32_t table;     // 1: window-table flavour (all windows of a job share one bucket set)
     uint32_t seg;       // slice length: entries per accumulate thread
     uint64_t stride;    // table flavour: entry = w * stride + i
+};
+
+// Several MSMs over the SAME bases (the commitments of one prover round share the SRS window table) run as ONE pipeline:
+// job j owns the bucket keys [j 2^(c-1), (j+1) 2^(c-1)), so that one sort, one accumulation and one reduction serve all of
+// them and each bucket set reduces to its own result.  Table flavour only (one bucket set per job); blockIdx.y = job.
+constexpr uint32_t MSM_MAX_JOBS = 8;
+struct MsmJobs {
+    const Fr* scalars[MSM_MAX_JOBS];
+    uint64_t n[MSM_MAX_JOBS];
+    uint32_t montgomery;  // bit j: the scalars of job j are Montgomery residues (a polynomial's coefficients)
+    uint32_t count;
 };
 
 __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, uint32_t pos, uint32_t c) {
@@ -63,10 +75,14 @@ __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, uint32_t pos,
 // (uniform scalars never collide, but skewed inputs -- equal scalars, a short top window -- would otherwise
 // serialise millions of atomics on a handful of L2 addresses).
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ scalars, uint64_t n, bool montgomery,
-                                                         MsmGeom g, uint32_t* __restrict__ counts_or_cursor,
+__global__ void __launch_bounds__(256) msm_digits_kernel(MsmJobs jobs, MsmGeom g, uint32_t* __restrict__ counts_or_cursor,
                                                          uint32_t* __restrict__ sorted) {
+    const uint32_t job = blockIdx.y;
+    const Fr* __restrict__ scalars = jobs.scalars[job];
+    const uint64_t n = jobs.n[job];
+    const bool montgomery = (jobs.montgomery >> job) & 1u;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((uint64_t)blockIdx.x * blockDim.x >= n) return;  // (whole block: the grid is sized for the longest job)
     const uint32_t lane = threadIdx.x & 31;
     Fr s = fp_zero<FrP>();  // lanes past the end run the loop with a zero scalar: the warp stays converged
     if (i < n) {
@@ -82,7 +98,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
     if (SCATTER) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
     uint32_t carry = 0;
     const uint32_t half = g.nbuckets;  // 2^(c-1)
-    const bool table = g.nsets == 1;
+    const bool table = g.table != 0;
     for (uint32_t w = 0; w < g.nwin; w++) {
         uint32_t raw = scalar_bits(s.l, w * g.c, g.c) + carry;
         uint32_t mag, neg;
@@ -96,25 +112,14 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
             carry = 0;
         }
         const bool valid = mag != 0;
-        const uint32_t key = valid ? (table ? 0u : w * g.nbuckets) + (mag - 1) : 0xffffffffu;
+        const uint32_t key = valid ? (table ? job * g.nbuckets : w * g.nbuckets) + (mag - 1) : 0xffffffffu;
         const uint32_t peers = __match_any_sync(0xffffffffu, key);
         const uint32_t leader = __ffs(peers) - 1;
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
         uint32_t base = 0;
-#ifdef KZG_MSM_EXPERIMENT
-        if (SCATTER && g.seg == 0xE1) {  // experiment 1: no returning atomic, pseudo-random store position
-            base = (uint32_t)(((uint64_t)key * 96u + (uint32_t)(i & 63)) % (n * g.nwin));
-        } else
-#endif
         if (valid && lane == leader) base = atomicAdd(&counts_or_cursor[key], (uint32_t)__popc(peers));
         if (SCATTER) {
             base = __shfl_sync(0xffffffffu, base, leader);
-#ifdef KZG_MSM_EXPERIMENT
-            if (g.seg == 0xE2) {  // experiment 2: returning atomic, coalesced store
-                if (valid) sorted[i * g.nwin + w] = base + rank;
-                continue;
-            }
-#endif
             if (valid) {
                 uint32_t entry = table ? (uint32_t)(w * g.stride + i) : (uint32_t)i;
                 // every bucket has ONE partially filled 32-byte sector of `sorted` at any time (2^(c-1) x 32 B in
@@ -266,6 +271,84 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan_apply_kernel(int mode, 
     }
 }
 
+// The bucket offsets of the sorted list AND of the list every batched-affine round leaves (ceil(count / 2^r) points per
+// bucket, r = 1 .. rounds) depend on the counts alone, so one set of three launches emits them all up front:
+// out[r * (nkeys + 1) + k], tile_sums[r * ntiles + tile].  Shift 0 also seeds the scatter cursors.
+constexpr uint32_t AFF_MAX_ROUNDS = 6;
+constexpr uint32_t MAX_SHIFTS = AFF_MAX_ROUNDS + 1;
+__global__ void __launch_bounds__(SCAN_THREADS) msm_offsets_tiles_kernel(const uint32_t* __restrict__ counts, uint32_t nkeys,
+                                                                         uint32_t nshift, uint32_t ntiles,
+                                                                         uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x;
+    uint32_t acc[MAX_SHIFTS];
+#pragma unroll
+    for (uint32_t r = 0; r < MAX_SHIFTS; r++) acc[r] = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        const uint32_t i = base + k * SCAN_THREADS;
+        const uint32_t c = i < nkeys ? counts[i] : 0u;
+#pragma unroll
+        for (uint32_t r = 0; r < MAX_SHIFTS; r++) acc[r] += (c + ((1u << r) - 1u)) >> r;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < MAX_SHIFTS; r++) {
+        if (r >= nshift) break;
+        uint32_t tot;
+        block_scan_u32(acc[r], sh, tot);
+        if (threadIdx.x == 0) tile_sums[r * ntiles + blockIdx.x] = tot;
+    }
+}
+// one block per shift: exclusive scan of its tile sums in place; grand total -> out[r][nkeys]
+__global__ void __launch_bounds__(SCAN_THREADS) msm_offsets_sums_kernel(uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+                                                                        uint32_t nkeys, uint32_t* __restrict__ out) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32];
+    __shared__ uint32_t carry_sh;
+    uint32_t* ts = tile_sums + (size_t)blockIdx.x * ntiles;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (uint32_t start = 0; start < ntiles; start += SCAN_THREADS) {
+        const uint32_t i = start + threadIdx.x;
+        const uint32_t v = i < ntiles ? ts[i] : 0;
+        uint32_t tot;
+        const uint32_t inc = block_scan_u32(v, sh, tot);
+        const uint32_t c = carry_sh;
+        if (i < ntiles) ts[i] = c + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_sh = c + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[(size_t)blockIdx.x * (nkeys + 1) + nkeys] = carry_sh;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) msm_offsets_apply_kernel(const uint32_t* __restrict__ counts, uint32_t nkeys,
+                                                                         uint32_t nshift, uint32_t ntiles,
+                                                                         const uint32_t* __restrict__ tile_sums,
+                                                                         uint32_t* __restrict__ out, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32];
+    // thread owns SCAN_PER_THREAD consecutive keys so that its partial results are a running sum
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t cnt[SCAN_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) cnt[k] = base + k < nkeys ? counts[base + k] : 0u;
+    for (uint32_t r = 0; r < nshift; r++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; k++) acc += (cnt[k] + ((1u << r) - 1u)) >> r;
+        uint32_t tot;
+        const uint32_t inc = block_scan_u32(acc, sh, tot);
+        uint32_t run = tile_sums[r * ntiles + blockIdx.x] + inc - acc;
+        uint32_t* o = out + (size_t)r * (nkeys + 1);
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; k++) {
+            if (base + k < nkeys) {
+                o[base + k] = run;
+                if (r == 0) cursor[base + k] = run;
+                run += (cnt[k] + ((1u << r) - 1u)) >> r;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Partition sort (large inputs): the same counts[] / offsets[] / sorted[] as the kernels above, without one global
 // atomic per entry.  218 M entries at 2^24 points cost 2 x 218 M L2 atomics plus as many scattered 4-byte stores in the
@@ -299,9 +382,9 @@ constexpr size_t CHUNK_SMEM = sizeof(uint32_t) * (SORT_CHUNK + 3 * (1u << SORT_M
 // signed c-bit digits of a scalar, least significant first: a 64-bit bit buffer is refilled limb by limb (static limb
 // indices: the scalar stays in registers), the windows beyond bit 255 see zeros plus the carry
 template <class F>
-__device__ __forceinline__ void msm_for_digits(const Fr& s, const MsmGeom& g, uint64_t i, F&& f) {
+__device__ __forceinline__ void msm_for_digits(const Fr& s, const MsmGeom& g, uint32_t key_base, uint64_t i, F&& f) {
     const uint32_t half = g.nbuckets, c = g.c, mask = (1u << g.c) - 1u;
-    const bool table = g.nsets == 1;
+    const bool table = g.table != 0;
     uint64_t buf = 0;
     uint32_t have = 0, w = 0, carry = 0;
     auto emit = [&]() {
@@ -318,7 +401,7 @@ __device__ __forceinline__ void msm_for_digits(const Fr& s, const MsmGeom& g, ui
             carry = 0;
         }
         if (mag != 0) {
-            const uint32_t key = (table ? 0u : w * half) + (mag - 1);
+            const uint32_t key = (table ? key_base : w * half) + (mag - 1);
             const uint32_t entry = table ? (uint32_t)(w * g.stride + i) : (uint32_t)i;
             f(key, entry | (neg << 31));
         }
@@ -345,16 +428,22 @@ __device__ __forceinline__ Fr load_scalar_stream(const Fr* scalars, uint64_t i, 
     return s;
 }
 
-__global__ void __launch_bounds__(PART_THREADS) msm_part_hist_kernel(const Fr* __restrict__ scalars, uint64_t n, bool montgomery,
-                                                                     MsmGeom g, SortGeom sg, uint32_t* __restrict__ part_hist) {
+__global__ void __launch_bounds__(PART_THREADS) msm_part_hist_kernel(MsmJobs jobs, MsmGeom g, SortGeom sg,
+                                                                     uint32_t* __restrict__ part_hist) {
     __shared__ uint32_t hist[SORT_MAX_PARTS];
+    const uint32_t job = blockIdx.y;
+    const Fr* __restrict__ scalars = jobs.scalars[job];
+    const uint64_t n = jobs.n[job];
+    const bool montgomery = (jobs.montgomery >> job) & 1u;
+    const uint64_t first = (uint64_t)blockIdx.x * sg.tile_scalars;
+    if (first >= n) return;
+    const uint32_t key_base = job * g.nbuckets;
     for (uint32_t p = threadIdx.x; p < sg.nparts; p += PART_THREADS) hist[p] = 0;
     __syncthreads();
-    const uint64_t first = (uint64_t)blockIdx.x * sg.tile_scalars;
     const uint64_t last = min(n, first + sg.tile_scalars);
     for (uint64_t i = first + threadIdx.x; i < last; i += PART_THREADS) {
         const Fr s = load_scalar_stream(scalars, i, montgomery);
-        msm_for_digits(s, g, i, [&](uint32_t key, uint32_t) { atomicAdd(&hist[key >> sg.low_bits], 1u); });
+        msm_for_digits(s, g, key_base, i, [&](uint32_t key, uint32_t) { atomicAdd(&hist[key >> sg.low_bits], 1u); });
     }
     __syncthreads();
     for (uint32_t p = threadIdx.x; p < sg.nparts; p += PART_THREADS)
@@ -432,10 +521,16 @@ __device__ __forceinline__ void block_exclusive_scan_smem(const uint32_t* cnt, u
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(PART_THREADS, 2) msm_part_scatter_kernel(const Fr* __restrict__ scalars, uint64_t n, bool montgomery,
-                                                                           MsmGeom g, SortGeom sg, uint32_t* __restrict__ part_cursor,
+__global__ void __launch_bounds__(PART_THREADS, 2) msm_part_scatter_kernel(MsmJobs jobs, MsmGeom g, SortGeom sg,
+                                                                           uint32_t* __restrict__ part_cursor,
                                                                            uint2* __restrict__ mid) {
     extern __shared__ __align__(16) unsigned char part_smem[];
+    const uint32_t job = blockIdx.y;
+    const Fr* __restrict__ scalars = jobs.scalars[job];
+    const uint64_t n = jobs.n[job];
+    const bool montgomery = (jobs.montgomery >> job) & 1u;
+    if ((uint64_t)blockIdx.x * sg.tile_scalars >= n) return;
+    const uint32_t key_base = job * g.nbuckets;
     uint2* stage = reinterpret_cast<uint2*>(part_smem);                                             // PART_TILE_ENTRIES pairs
     uint16_t* ranks = reinterpret_cast<uint16_t*>(part_smem + sizeof(uint2) * PART_TILE_ENTRIES);   // rank of every digit in its partition
     uint32_t* hist = reinterpret_cast<uint32_t*>(part_smem + (sizeof(uint2) + sizeof(uint16_t)) * PART_TILE_ENTRIES);
@@ -454,7 +549,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2) msm_part_scatter_kernel(const
         if (i < last) {
             sc[k] = load_scalar_stream(scalars, i, montgomery);
             uint32_t slot = local * g.nwin;  // one slot per (scalar, window)
-            msm_for_digits(sc[k], g, i, [&](uint32_t key, uint32_t) {
+            msm_for_digits(sc[k], g, key_base, i, [&](uint32_t key, uint32_t) {
                 ranks[slot++] = (uint16_t)atomicAdd(&hist[key >> sg.low_bits], 1u);
             });
         }
@@ -472,7 +567,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2) msm_part_scatter_kernel(const
         const uint64_t i = first + local;
         if (i < last) {
             uint32_t slot = local * g.nwin;
-            msm_for_digits(sc[k], g, i, [&](uint32_t key, uint32_t entry) {
+            msm_for_digits(sc[k], g, key_base, i, [&](uint32_t key, uint32_t entry) {
                 stage[loff[key >> sg.low_bits] + ranks[slot++]] = make_uint2(entry, key);
             });
         }
@@ -822,10 +917,10 @@ __device__ __forceinline__ Fq aff_load_x(const AffRound& a, uint32_t h) {
 }
 
 template <bool INDEXED>
-__global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRound a, uint32_t m, Fq* __restrict__ prefix,
-                                                                         Fq* __restrict__ totals) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.nthreads) return;
+__global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRound a, uint32_t m, uint32_t t_first, uint32_t t_end,
+                                                                         Fq* __restrict__ prefix, Fq* __restrict__ totals) {
+    const uint32_t t = t_first + blockIdx.x * blockDim.x + threadIdx.x;  // (a round is launched in chunks of threads)
+    if (t >= t_end) return;
     Fq acc = fp_one<FqP>();
     const uint32_t total = a.off_out[a.nkeys];
     const uint64_t begin64 = (uint64_t)t * m;
@@ -877,11 +972,12 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRoun
 }
 
 template <bool INDEXED>
-__global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRound a, uint32_t m, const Fq* __restrict__ prefix,
+__global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRound a, uint32_t m, uint32_t t_first, uint32_t t_end,
+                                                                          const Fq* __restrict__ prefix,
                                                                           const Fq* __restrict__ inv_totals,
                                                                           Fq* __restrict__ out_x, Fq* __restrict__ out_y) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.nthreads) return;
+    const uint32_t t = t_first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_end) return;
     const uint32_t total = a.off_out[a.nkeys];
     const uint64_t begin64 = (uint64_t)t * m;
     if (begin64 >= total) return;
@@ -1246,6 +1342,26 @@ __global__ void msm_horner_kernel(const G1XYZZ* __restrict__ windows, uint32_t n
     store_xyzz(result, acc);
 }
 
+// sum `count` XYZZ points into one XYZZ point (the pieces of a host-scalar shard before the all-gather): one warp,
+// quad-lane arithmetic as in g1_finish
+__global__ void __launch_bounds__(32) g1_sum_kernel(const G1XYZZ* __restrict__ parts, uint32_t count, G1XYZZ* __restrict__ out) {
+    if (blockIdx.x != 0) return;
+    const uint32_t lane = threadIdx.x & 31, j = lane & 3;
+    if (count == 1) {
+        if (lane == 0) store_xyzz(out, load_xyzz(parts));
+        return;
+    }
+    const uint32_t qm = quad_mask();
+    Fq a = fp_zero<FqP>();
+#pragma unroll 1
+    for (uint32_t k = lane >> 2; k < count; k += 8) {
+        const Fq o = quad_load(parts + k, j);
+        quad_add(a, o, j, qm);
+    }
+    quad_butterfly(a, 16, j, qm);
+    if (lane < 4) quad_store(out, j, a);
+}
+
 // sum `count` XYZZ points and write the canonical affine encoding.  One warp: the partial points (the shards of a
 // multi-GPU MSM, the pieces of a host-scalar MSM) are summed in quad-lane arithmetic -- 8 quads stride over them, then a
 // 3-level butterfly -- and lane 0 does the one inversion.
@@ -1354,9 +1470,6 @@ static uint32_t auto_window_raw(uint64_t n) {
 //   + 4.6 * 2^(c-1)               bucket reduction (measured: 0.64 ms at 2^19 buckets, 1.96 ms at 2^21, ~0.25 ms of it
 //                                 independent of the bucket count)
 constexpr uint64_t PART_SORT_MIN_ENTRIES = 1ull << 22;
-constexpr uint64_t AFF_MIN_ENTRIES = 48ull << 20;  // from 2^22 points on (13 digits each)
-constexpr uint64_t AFF_MIN_LEFT = 1ull << 23;
-constexpr uint32_t AFF_MAX_ROUNDS = 6;
 uint32_t msm_table_window(uint64_t n) {
     uint32_t best = 4;
     double best_cost = 1e300;
@@ -1386,13 +1499,14 @@ uint32_t msm_table_window(uint64_t n) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static MsmGeom msm_geometry(kzg_ctx* ctx, const MsmBases& b, uint64_t n, bool montgomery) {
+static MsmGeom msm_geometry(kzg_ctx* ctx, const MsmBases& b, uint64_t n, bool montgomery, uint32_t njobs = 1) {
     MsmGeom g;
     if (b.table) {
         g.c = b.tab_c;
         g.nwin = windows_for(g.c, montgomery);
         if (g.nwin > b.tab_nwin) g.nwin = b.tab_nwin;  // (never: the table is built for raw scalars)
-        g.nsets = 1;
+        g.nsets = njobs;
+        g.table = 1;
         g.stride = b.stride;
     } else {
         g.c = ctx->msm_window ? ctx->msm_window : auto_window_raw(n);
@@ -1400,6 +1514,7 @@ static MsmGeom msm_geometry(kzg_ctx* ctx, const MsmBases& b, uint64_t n, bool mo
         if (g.c > 22) g.c = 22;
         g.nwin = windows_for(g.c, montgomery);
         g.nsets = g.nwin;
+        g.table = 0;
         g.stride = 0;
     }
     g.nbuckets = 1u << (g.c - 1);
@@ -1407,50 +1522,80 @@ static MsmGeom msm_geometry(kzg_ctx* ctx, const MsmBases& b, uint64_t n, bool mo
     return g;
 }
 
-// batched-affine rounds before the XYZZ walk.  Measured on B200 (profiles/r01_msm_affine.md): a round over DENSE
-// points runs at 0.09 ns per addition against 0.16 ns for the XYZZ walk, but round 1 gathers its operands from the
-// window table twice (x for the denominators, then the points) at 128 B of DRAM traffic per 64-byte point and only
-// breaks even, and every round pays ~0.25 ms of latency-bound launches (scan, the tail of the batch inversion).
-// So: a round only while the list it produces keeps >= 2^23 points and its buckets hold >= 6 entries on average.
-static uint32_t msm_affine_rounds(uint64_t max_entries, uint32_t nkeys) {
+// batched-affine rounds before the XYZZ walk.  Measured on B200 (profiles/r01_msm_affine.md, r02_msm_small.md): a round
+// over DENSE points runs at 0.10-0.12 ns per addition against 0.16-0.17 ns for the XYZZ walk; round 1 gathers its operands
+// from the window table twice (x for the denominators, then the points) and is bound by the rate of random 32-byte
+// sectors (44 G/s whatever the table size beyond the L2, tools/micro/gather.cu sweep): 0.15 ns.  The inversion of a round
+// is a chain of ~8 small launches (0.13-0.2 ms): it runs on a high-priority side stream under the forward pass of the
+// round's later chunks, so what a round still pays is its scan-free launch overhead.  A round is worth it while its
+// buckets hold >= aff_min_fill entries on average and the list it leaves keeps >= aff_min_left points.
+static uint32_t msm_affine_rounds(kzg_ctx* ctx, uint64_t max_entries, uint32_t nkeys) {
+    const MsmTuning& tn = ctx->tuning;
     uint32_t aff_rounds = 0;
-    if (max_entries >= AFF_MIN_ENTRIES) {
+    if (max_entries >= tn.aff_min_entries) {
         double fill = (double)max_entries / nkeys;
         uint64_t left = max_entries / 2;
-        while (aff_rounds < AFF_MAX_ROUNDS && fill >= 6.0 && left >= AFF_MIN_LEFT) {
+        while (aff_rounds < AFF_MAX_ROUNDS && fill >= tn.aff_min_fill && left >= tn.aff_min_left) {
             aff_rounds++;
             fill *= 0.5;
             left /= 2;
         }
     }
-    if (const char* ov = getenv("KZGB200_AFF_ROUNDS")) {  // tuning / A-B tests
-        aff_rounds = (uint32_t)atoi(ov);
-        if (aff_rounds > AFF_MAX_ROUNDS) aff_rounds = AFF_MAX_ROUNDS;
-    }
+    if (tn.aff_rounds >= 0) aff_rounds = tn.aff_rounds > (int)AFF_MAX_ROUNDS ? AFF_MAX_ROUNDS : (uint32_t)tn.aff_rounds;
     return aff_rounds;
 }
 
-int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev) {
-    if (n == 0) {
-        KZG_CUDA(ctx, cudaMemsetAsync(result_dev, 0, sizeof(G1XYZZ), ctx->stream));
+// an event for stream-to-stream ordering inside one call, from a per-context ring (no timing, never destroyed before
+// the context is): a wait captures the state of the event when it is enqueued, so a slot can be re-recorded later
+static cudaEvent_t order_event(kzg_ctx* ctx) {
+    if (ctx->order_events.size() < 256) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        ctx->order_events.push_back(e);
+        return e;
+    }
+    ctx->order_next = (ctx->order_next + 1) % ctx->order_events.size();
+    return ctx->order_events[ctx->order_next];
+}
+
+// `jobs.count` MSMs over the same bases as one pipeline; results[j] receives the XYZZ sum of job j (device memory).
+// More than one job needs the window-table flavour.
+int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XYZZ* results) {
+    const uint32_t njobs = jobs.count;
+    if (njobs == 0) return KZG_OK;
+    if (njobs > MSM_MAX_JOBS) return set_err(ctx, KZG_ERR_ARG, "msm: too many jobs in one pipeline");
+    if (njobs > 1 && !bases.table) return set_err(ctx, KZG_ERR_ARG, "msm: merged jobs need the SRS window table");
+    uint64_t n = 0, total_n = 0;  // longest job, all jobs
+    bool any_std = false;
+    for (uint32_t j = 0; j < njobs; j++) {
+        if (jobs.n[j] > n) n = jobs.n[j];
+        total_n += jobs.n[j];
+        if (!((jobs.montgomery >> j) & 1u)) any_std = true;
+    }
+    if (total_n == 0) {
+        KZG_CUDA(ctx, cudaMemsetAsync(results, 0, sizeof(G1XYZZ) * njobs, ctx->stream));
         return KZG_OK;
     }
     if (n >= (1ull << 27)) return set_err(ctx, KZG_ERR_ARG, "msm: at most 2^27 - 1 points per call");
-    MsmGeom g = msm_geometry(ctx, bases, n, src.montgomery);
+    const MsmTuning& tn = ctx->tuning;
+    // (standard-form scalars may use all 256 bits: one digit more than Montgomery residues at some window sizes; a
+    // merged pipeline uses the larger count for all its jobs -- the extra digit of a reduced scalar is zero)
+    MsmGeom g = msm_geometry(ctx, bases, n, !any_std, njobs);
     const uint32_t nkeys = g.nsets * g.nbuckets;
-    const uint64_t max_entries = n * g.nwin;
+    const uint64_t max_entries = total_n * g.nwin;
     if (max_entries >= (1ull << 32)) return set_err(ctx, KZG_ERR_ARG, "msm: n * windows exceeds 2^32 entries");
-    const uint32_t aff_rounds = msm_affine_rounds(max_entries, nkeys);
-    uint32_t aff_m = AFF_M;  // output points per thread of a round
-    if (const char* ov = getenv("KZGB200_AFF_M")) {
-        aff_m = (uint32_t)atoi(ov);
-        if (aff_m < 1) aff_m = 1;
-        if (aff_m > 256) aff_m = 256;
-    }
+    if ((uint64_t)nkeys >= (1ull << 31)) return set_err(ctx, KZG_ERR_ARG, "msm: too many bucket keys");
+    const uint32_t aff_rounds = msm_affine_rounds(ctx, max_entries, nkeys);
+    const uint32_t aff_m = tn.aff_m;  // output points per thread of a round
     // upper bounds of the list lengths: sum_b ceil(k_b / 2) <= (entries + buckets) / 2
     uint64_t aff_entries[AFF_MAX_ROUNDS + 1];
     aff_entries[0] = max_entries;
-    for (uint32_t r = 1; r <= aff_rounds; r++) aff_entries[r] = (aff_entries[r - 1] + nkeys) / 2 + 1;
+    // (and a list never grows: with more buckets than entries the first bound alone would exceed the previous length,
+    // and the prefix / thread-product arrays are sized by round 1)
+    for (uint32_t r = 1; r <= aff_rounds; r++) {
+        aff_entries[r] = (aff_entries[r - 1] + nkeys) / 2 + 1;
+        if (aff_entries[r] > aff_entries[r - 1]) aff_entries[r] = aff_entries[r - 1];
+    }
     const uint64_t walk_entries = aff_entries[aff_rounds];  // what the XYZZ walk sees
     // slice length: a few average buckets (every slice start costs one extra partial sum), but short enough to
     // give every SM several waves of equal-sized tasks
@@ -1468,7 +1613,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     TailGeom tg;
     // (measured: 2^19 buckets 0.59 ms with chunks of 16 against 0.62 with 8, 2^21 buckets 1.54 against 1.63)
     tg.k0 = (uint64_t)g.nbuckets * g.nsets >= (1u << 19) ? 4 : 2;
-    if (const char* ov = getenv("KZGB200_RED_K0")) tg.k0 = (uint32_t)atoi(ov);  // tuning
+    if (tn.red_k0 >= 0) tg.k0 = (uint32_t)tn.red_k0;
     if (tg.k0 > 6) tg.k0 = 6;
     while (tg.k0 > 0 && (1u << tg.k0) > g.nbuckets) tg.k0--;
     tg.n1 = (g.nbuckets + (1u << tg.k0) - 1) >> tg.k0;
@@ -1479,9 +1624,11 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     tg.ntask = tg.lo + 2 * tg.hi;
 
     // scratch layout
+    const uint32_t nshift = aff_rounds + 1;
+    const uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
     size_t off = 0;
     const size_t o_counts = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
-    const size_t o_offsets = off;  off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
+    const size_t o_offsets = off;  off = align_up(off + sizeof(uint32_t) * (nkeys + 1) * nshift, 256);  // [shift][nkeys + 1]
     const size_t o_cursor = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_segoff = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_sorted = off;   off = align_up(off + sizeof(uint32_t) * max_entries, 256);
@@ -1490,17 +1637,14 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     const size_t o_tv = off;       off = align_up(off + sizeof(G1XYZZ) * tg.n1 * g.nsets, 256);
     const size_t o_lp = off;       off = align_up(off + sizeof(G1XYZZ) * tg.ntask * g.nsets, 256);
     const size_t o_sets = off;     off = align_up(off + sizeof(G1XYZZ) * g.nsets, 256);
-    const uint32_t ntiles = (nkeys + SCAN_TILE - 1) / SCAN_TILE;
-    const size_t o_tiles = off;    off = align_up(off + sizeof(uint32_t) * ntiles, 256);
+    const size_t o_tiles = off;    off = align_up(off + sizeof(uint32_t) * ntiles * nshift, 256);
     const size_t o_heavy = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_multi = off;    off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
     const size_t o_huge = off;     off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
-    // batched-affine rounds: two offset arrays and two point lists (ping-pong), prefix products, thread products
-    size_t o_aff_off[2] = {0, 0}, o_aff_pts[2] = {0, 0}, o_aff_prefix = 0, o_aff_totals = 0;
+    // batched-affine rounds: two point lists (ping-pong), prefix products, thread products
+    size_t o_aff_pts[2] = {0, 0}, o_aff_prefix = 0, o_aff_totals = 0;
     if (aff_rounds) {
         const uint64_t threads1 = (aff_entries[1] + aff_m - 1) / aff_m;
-        o_aff_off[0] = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
-        o_aff_off[1] = off;   off = align_up(off + sizeof(uint32_t) * (nkeys + 1), 256);
         o_aff_pts[0] = off;   off = align_up(off + sizeof(G1Affine) * aff_entries[1], 256);
         o_aff_pts[1] = off;   off = align_up(off + sizeof(G1Affine) * (aff_rounds > 1 ? aff_entries[2] : 0), 256);
         o_aff_prefix = off;   off = align_up(off + sizeof(Fq) * threads1 * aff_m, 256);
@@ -1511,7 +1655,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     memset(&sg, 0, sizeof(sg));
     // (measured on B200: 0.24 vs 0.32 ms at 2^20 points, 0.74 vs 1.11 ms at 2^22, 2.9 vs 5.7 ms at 2^24; level below 2^18)
     bool use_part_sort = max_entries >= PART_SORT_MIN_ENTRIES;
-    if (const char* ov = getenv("KZGB200_PART_SORT")) use_part_sort = atoi(ov) != 0;  // tuning / A-B tests
+    if (tn.part_sort >= 0) use_part_sort = tn.part_sort != 0;
     uint32_t max_chunks = 0;
     size_t o_mid = 0, o_phist = 0, o_pstart = 0, o_pcursor = 0, o_cstart = 0, o_chist = 0;
     if (use_part_sort) {
@@ -1531,7 +1675,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         }
     }
     if (use_part_sort) {
-        sg.ntiles = (uint32_t)((n + sg.tile_scalars - 1) / sg.tile_scalars);
+        sg.ntiles = (uint32_t)((n + sg.tile_scalars - 1) / sg.tile_scalars);  // per job (grid.x; grid.y = job)
         max_chunks = sg.nparts + (uint32_t)(max_entries / SORT_CHUNK) + 1;
         o_mid = off;     off = align_up(off + sizeof(uint2) * max_entries, 256);
         o_phist = off;   off = align_up(off + sizeof(uint32_t) * (sg.nparts + 1), 256);
@@ -1569,7 +1713,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     KZG_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(multi, 0, sizeof(uint32_t), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(huge, 0, sizeof(uint32_t), ctx->stream));
-    const uint32_t dblocks = (uint32_t)((n + 255) / 256);
+    const dim3 dgrid((uint32_t)((n + 255) / 256), njobs);
     timed_begin(ctx, KZG_TIMED_MSM_SORT);
     if (use_part_sort) {
         static const size_t part_smem_max = (sizeof(uint2) + sizeof(uint16_t)) * PART_TILE_ENTRIES + sizeof(uint32_t) * (3 * SORT_MAX_PARTS + 2);
@@ -1580,42 +1724,43 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
             KZG_CUDA(ctx, cudaFuncSetAttribute(msm_chunk_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHUNK_SMEM));
             attr_set[ctx->device & 63] = true;
         }
+        const dim3 tgrid(sg.ntiles, njobs);
         KZG_CUDA(ctx, cudaMemsetAsync(part_hist, 0, sizeof(uint32_t) * (sg.nparts + 1), ctx->stream));
-        KZG_LAUNCH(ctx, msm_part_hist_kernel, sg.ntiles, PART_THREADS, 0, src.scalars, n, src.montgomery, g, sg, part_hist);
+        KZG_LAUNCH(ctx, msm_part_hist_kernel, tgrid, PART_THREADS, 0, jobs, g, sg, part_hist);
         KZG_LAUNCH(ctx, msm_part_scan_kernel, 1, SCAN_THREADS, 0, part_hist, sg.nparts, pstart, part_cursor, cstart);
-        KZG_LAUNCH(ctx, msm_part_scatter_kernel, sg.ntiles, PART_THREADS, part_smem, src.scalars, n, src.montgomery, g, sg,
-                   part_cursor, mid);
+        KZG_LAUNCH(ctx, msm_part_scatter_kernel, tgrid, PART_THREADS, part_smem, jobs, g, sg, part_cursor, mid);
         KZG_LAUNCH(ctx, msm_chunk_hist_kernel, max_chunks, CHUNK_THREADS, 0, mid, pstart, cstart, sg, counts, chunk_hist);
     } else {
-        KZG_LAUNCH(ctx, msm_digits_kernel<false>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, counts, nullptr);
+        KZG_LAUNCH(ctx, msm_digits_kernel<false>, dgrid, 256, 0, jobs, g, counts, nullptr);
     }
-    // exclusive scan of ceil(count / 2^shift) over the keys -> out[0 .. nkeys]
-    auto scan_offsets = [&](uint32_t shift, uint32_t* out, uint32_t* cursor_out) {
-        KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, shift,
-                   tile_sums);
-        KZG_LAUNCH(ctx, msm_scan_sums_kernel, 1, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, out);
-        KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 0, counts, (const uint32_t*)nullptr, nkeys, g.seg, shift,
-                   tile_sums, out, cursor_out, heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
-    };
-    scan_offsets(0, offsets, cursor);
+    // bucket offsets of the sorted list and of every round's output list (one scan set for all of them)
+    KZG_LAUNCH(ctx, msm_offsets_tiles_kernel, ntiles, SCAN_THREADS, 0, counts, nkeys, nshift, ntiles, tile_sums);
+    KZG_LAUNCH(ctx, msm_offsets_sums_kernel, nshift, SCAN_THREADS, 0, tile_sums, ntiles, nkeys, offsets);
+    KZG_LAUNCH(ctx, msm_offsets_apply_kernel, ntiles, SCAN_THREADS, 0, counts, nkeys, nshift, ntiles, tile_sums, offsets, cursor);
     if (use_part_sort)
         KZG_LAUNCH(ctx, msm_chunk_scatter_kernel, max_chunks, CHUNK_THREADS, CHUNK_SMEM, mid, pstart, cstart, sg, chunk_hist, cursor,
                    sorted);
     else
-        KZG_LAUNCH(ctx, msm_digits_kernel<true>, dblocks, 256, 0, src.scalars, n, src.montgomery, g, cursor, sorted);
+        KZG_LAUNCH(ctx, msm_digits_kernel<true>, dgrid, 256, 0, jobs, g, cursor, sorted);
     timed_end(ctx, KZG_TIMED_MSM_SORT);
 
-    // batched-affine rounds: (sorted, offsets) -> dense point lists, half as long each time
+    // batched-affine rounds: (sorted, offsets) -> dense point lists, half as long each time.  A round is launched in
+    // chunks of threads: all forward chunks first, each followed by the inversion of ITS thread products on the lane's
+    // high-priority side stream, then the backward chunks, each waiting for its own inversion only -- the latency-bound
+    // inversion chains (~8 small launches) run under the remaining forward chunks and the earlier backward chunks.
     const uint32_t* walk_offsets = offsets;
     const Fq *walk_x = nullptr, *walk_y = nullptr;  // the dense list the rounds leave: a plane of x and a plane of y
     if (aff_rounds) timed_begin(ctx, KZG_TIMED_MSM_AFFINE);
-    for (uint32_t r = 1; r <= aff_rounds; r++) {
-        uint32_t* off_out = (uint32_t*)(sc + o_aff_off[r & 1]);
+    cudaStream_t main_stream = ctx->stream;
+    cudaStream_t side_stream = ctx->side_stream[ctx->lane];
+    cudaStream_t inv_stream = ctx->inv_stream[ctx->lane];
+    int rr = KZG_OK;
+    for (uint32_t r = 1; r <= aff_rounds && rr == KZG_OK; r++) {
+        uint32_t* off_out = offsets + (size_t)r * (nkeys + 1);
         Fq* out_x = (Fq*)(sc + o_aff_pts[(r & 1) ^ 1]);
         Fq* out_y = out_x + aff_entries[(r & 1) ? 1 : 2];  // (capacity of that buffer in points)
         Fq* prefix = (Fq*)(sc + o_aff_prefix);
         Fq* totals = (Fq*)(sc + o_aff_totals);
-        scan_offsets(r, off_out, cursor);  // (the scatter is done with `cursor`: free scratch)
         AffRound ar;
         ar.bases = pts;
         ar.sorted = r == 1 ? sorted : nullptr;
@@ -1625,21 +1770,101 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         ar.off_out = off_out;
         ar.nkeys = nkeys;
         ar.nthreads = (uint32_t)((aff_entries[r] + aff_m - 1) / aff_m);
-        const uint32_t blocks = (ar.nthreads + AFF_THREADS - 1) / AFF_THREADS;
-        if (r == 1)
-            KZG_LAUNCH(ctx, msm_aff_forward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals);
-        else
-            KZG_LAUNCH(ctx, msm_aff_forward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals);
-        KZG_TRY(fq_batch_inverse(ctx, totals, totals, ar.nthreads));
-        if (r == 1)
-            KZG_LAUNCH(ctx, msm_aff_backward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals, out_x, out_y);
-        else
-            KZG_LAUNCH(ctx, msm_aff_backward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, prefix, totals, out_x, out_y);
+        // Chunks of threads, a multiple of the block size each, alternating between the lane's main stream and its side
+        // stream: consecutive kernels of ONE stream do not overlap, so with all chunks on one stream every chunk would
+        // expose its own tail (a block lives ~90 us: measured +1.6 ms at 2^24 points with 4 chunks per round); on two
+        // streams the next chunk's blocks fill the previous chunk's tail.
+        uint32_t nchunks = tn.aff_chunks > 0 ? (uint32_t)tn.aff_chunks : 2;
+        const uint32_t min_chunk_threads = (uint32_t)ctx->sm_count * AFF_THREADS * 8;
+        while (nchunks > 1 && ar.nthreads / nchunks < min_chunk_threads) nchunks--;
+        if (nchunks > 16) nchunks = 16;
+        uint32_t chunk_threads = (ar.nthreads + nchunks - 1) / nchunks;
+        chunk_threads = (chunk_threads + AFF_THREADS - 1) / AFF_THREADS * AFF_THREADS;
+        nchunks = (ar.nthreads + chunk_threads - 1) / chunk_threads;
+        const bool piped = nchunks > 1;
+        cudaEvent_t inv_done[16];
+        auto mark = [&](cudaStream_t st, const char* what, uint32_t k) {  // KZGB200_TIMELINE=1: where does a round's time go
+            if (!tn.timeline) return;
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            char label[64];
+            snprintf(label, sizeof(label), "r%u %s%u", r, what, k);
+            ctx->timeline.push_back({e, label});
+        };
+        mark(main_stream, "round_begin", 0);
+        if (piped) {  // the side stream joins in: everything queued so far (the previous round) is its input too
+            cudaEvent_t fork = order_event(ctx);
+            cudaEventRecord(fork, main_stream);
+            cudaStreamWaitEvent(side_stream, fork, 0);
+        }
+        for (uint32_t k = 0; k < nchunks; k++) {
+            const uint32_t t0 = k * chunk_threads;
+            const uint32_t t1 = t0 + chunk_threads < ar.nthreads ? t0 + chunk_threads : ar.nthreads;
+            const uint32_t blocks = (t1 - t0 + AFF_THREADS - 1) / AFF_THREADS;
+            ctx->stream = (k & 1) ? side_stream : main_stream;
+            if (r == 1)
+                KZG_LAUNCH(ctx, msm_aff_forward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals);
+            else
+                KZG_LAUNCH(ctx, msm_aff_forward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals);
+            mark(ctx->stream, "F_end", k);
+            if (piped) {
+                cudaEvent_t fwd_done = order_event(ctx);
+                inv_done[k] = order_event(ctx);
+                cudaEventRecord(fwd_done, ctx->stream);
+                cudaStreamWaitEvent(inv_stream, fwd_done, 0);
+                ctx->stream = inv_stream;
+                mark(inv_stream, "I_begin", k);
+                rr = fq_batch_inverse(ctx, totals + t0, totals + t0, t1 - t0);
+                mark(inv_stream, "I_end", k);
+                cudaEventRecord(inv_done[k], inv_stream);
+                if (rr != KZG_OK) {
+                    nchunks = k + 1;
+                    break;
+                }
+            } else {
+                rr = fq_batch_inverse(ctx, totals, totals, ar.nthreads);
+            }
+        }
+        for (uint32_t k = 0; k < nchunks; k++) {
+            const uint32_t t0 = k * chunk_threads;
+            const uint32_t t1 = t0 + chunk_threads < ar.nthreads ? t0 + chunk_threads : ar.nthreads;
+            const uint32_t blocks = (t1 - t0 + AFF_THREADS - 1) / AFF_THREADS;
+            ctx->stream = (k & 1) ? side_stream : main_stream;
+            if (piped) cudaStreamWaitEvent(ctx->stream, inv_done[k], 0);  // (also on the error path: the inversion stream drains)
+            if (rr != KZG_OK) continue;
+            mark(ctx->stream, "B_begin", k);
+            if (r == 1)
+                KZG_LAUNCH(ctx, msm_aff_backward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, out_x, out_y);
+            else
+                KZG_LAUNCH(ctx, msm_aff_backward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, out_x, out_y);
+            mark(ctx->stream, "B_end", k);
+        }
+        ctx->stream = main_stream;
+        if (piped) {  // join: the main stream continues after the side stream's chunks
+            cudaEvent_t join = order_event(ctx);
+            cudaEventRecord(join, side_stream);
+            cudaStreamWaitEvent(main_stream, join, 0);
+        }
         walk_offsets = off_out;
         walk_x = out_x;
         walk_y = out_y;
     }
+    KZG_TRY(rr);
     if (aff_rounds) timed_end(ctx, KZG_TIMED_MSM_AFFINE);
+    if (tn.timeline && !ctx->timeline.empty()) {
+        cudaStreamSynchronize(main_stream);
+        cudaStreamSynchronize(inv_stream);
+        cudaStreamSynchronize(side_stream);
+        for (auto& m : ctx->timeline) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ctx->timeline[0].first, m.first);
+            fprintf(stderr, "[timeline] %-16s %8.3f ms\n", m.second.c_str(), t);
+            if (&m != &ctx->timeline[0]) cudaEventDestroy(m.first);
+        }
+        cudaEventDestroy(ctx->timeline[0].first);
+        ctx->timeline.clear();
+    }
 
     // partial-sum slots of the XYZZ walk over what is left
     KZG_LAUNCH(ctx, msm_scan_tiles_kernel, ntiles, SCAN_THREADS, 0, 1, counts, walk_offsets, nkeys, g.seg, aff_rounds, tile_sums);
@@ -1664,7 +1889,8 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
         const uint64_t max_multi = max_tasks < nkeys ? max_tasks : nkeys;
         KZG_LAUNCH(ctx, msm_fold_kernel, (uint32_t)((max_multi + 127) / 128), 128, 0, partials, segoff, multi + 1, multi);
     }
-    G1XYZZ* sums_out = g.nsets == 1 ? result_dev : set_sums;
+    // table flavour: every bucket set IS a result (one per job); raw flavour: the sets are the windows of one result
+    G1XYZZ* sums_out = g.table ? results : set_sums;
     {
         const dim3 grid((tg.n1 + RED_THREADS - 1) / RED_THREADS, g.nsets);
         // (measured: calling the shared addition at 126 registers / 16 warps per SM beats the inlined 168-register
@@ -1675,7 +1901,7 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     {
         // task width: all the tasks should be resident at once (one wave)
         int width = (uint64_t)tg.ntask * g.nsets > (uint64_t)ctx->sm_count * 3 ? 64 : 128;
-        if (const char* ov = getenv("KZGB200_TAIL_WIDTH")) width = atoi(ov);  // tuning
+        if (tn.tail_width > 0) width = tn.tail_width;
         if (width == 32)
             KZG_LAUNCH(ctx, msm_tail_tasks_kernel<32>, dim3(tg.ntask, g.nsets), 32, 0, u_arrays, tvals, tg, tail_parts);
         else if (width == 64)
@@ -1684,31 +1910,20 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
             KZG_LAUNCH(ctx, msm_tail_tasks_kernel<128>, dim3(tg.ntask, g.nsets), 128, 0, u_arrays, tvals, tg, tail_parts);
     }
     KZG_LAUNCH(ctx, msm_tail_final_kernel, g.nsets, 256, 0, tail_parts, tg, sums_out);
-    if (g.nsets > 1) KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, result_dev);
+    if (!g.table) KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, results);
     timed_end(ctx, KZG_TIMED_MSM_REDUCE);
-#ifdef KZG_MSM_EXPERIMENT
-    if (getenv("KZG_MSM_EXPERIMENT")) {  // timing experiments on the scatter kernel (results are then discarded)
-        MsmGeom ge = g;
-        cudaEvent_t e0, e1, e2;
-        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-        cudaMemcpyAsync(cursor, offsets, sizeof(uint32_t) * nkeys, cudaMemcpyDeviceToDevice, ctx->stream);
-        cudaEventRecord(e0, ctx->stream);
-        ge.seg = 0xE1;
-        msm_digits_kernel<true><<<dblocks, 256, 0, ctx->stream>>>(src.scalars, n, src.montgomery, ge, cursor, sorted);
-        cudaEventRecord(e1, ctx->stream);
-        ge.seg = 0xE2;
-        msm_digits_kernel<true><<<dblocks, 256, 0, ctx->stream>>>(src.scalars, n, src.montgomery, ge, cursor, sorted);
-        cudaEventRecord(e2, ctx->stream);
-        cudaEventSynchronize(e2);
-        float t1, t2;
-        cudaEventElapsedTime(&t1, e0, e1);
-        cudaEventElapsedTime(&t2, e1, e2);
-        fprintf(stderr, "[msm experiment] n=%llu: scattered stores without atomics %.3f ms; returning atomics with coalesced stores %.3f ms\n",
-                (unsigned long long)n, t1, t2);
-    }
-#endif
     KZG_CHECK_LAUNCH(ctx);
     return KZG_OK;
+}
+
+int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev) {
+    MsmJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    jobs.scalars[0] = src.scalars;
+    jobs.n[0] = n;
+    jobs.montgomery = src.montgomery ? 1u : 0u;
+    jobs.count = 1;
+    return msm_run_multi(ctx, bases, jobs, result_dev);
 }
 
 int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t count, uint8_t out[64]) {
@@ -1742,8 +1957,8 @@ int msm_run_split(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_
     // 2^23 points before the batched-affine rounds; with them one undivided MSM is faster everywhere (2^23: 18.5 vs
     // 20.0 ms, 2^24: 33.7 vs 35.7 ms, 2^22: 9.8 vs 11.1 ms), so the range is empty unless set for an experiment.
     uint64_t split_min = 0, split_max = 0;  // split when split_min < n <= split_max
-    if (const char* ov = getenv("KZGB200_SPLIT_MIN_LOG")) split_min = 1ull << atoi(ov);  // tuning / A-B tests
-    if (const char* ov = getenv("KZGB200_SPLIT_MAX_LOG")) split_max = 1ull << atoi(ov);
+    if (ctx->tuning.split_min_log >= 0) split_min = 1ull << ctx->tuning.split_min_log;
+    if (ctx->tuning.split_max_log >= 0) split_max = 1ull << ctx->tuning.split_max_log;
     if (n <= split_min || n > split_max || ctx->lane != 0 || ctx->no_split) return msm_run(ctx, bases, src, n, result_dev);
     const uint64_t h = n / 2;
     G1XYZZ* halves = (G1XYZZ*)(ctx->dev_small + 12288);
@@ -1769,30 +1984,66 @@ int msm_run_split(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_
     return KZG_OK;
 }
 
-// Independent MSMs (the commitments of one prover round): MSM i is issued on lane i & 1 -- lane 1 is the
-// context's auxiliary stream with its own scratch arena -- so that the latency-bound tail of one (bucket
-// reduction, inversion) overlaps the pipe-bound bucket accumulation of the other.  Every job leaves its affine
-// result in its own 64-byte slot; one D2H copy and one synchronisation fetch them all.
+// count affine results out of count XYZZ sums, one warp each (lane 0 of the warp does the inversion)
+__global__ void __launch_bounds__(32) g1_finish_many_kernel(const G1XYZZ* __restrict__ sums, G1Affine* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    const G1XYZZ acc = load_xyzz(sums + blockIdx.x);
+    const G1Affine r = xyzz_to_affine(acc);
+    fp_store(&out[blockIdx.x].x, r.x);
+    fp_store(&out[blockIdx.x].y, r.y);
+}
+
+// Independent MSMs (the commitments of one prover round).  Jobs that share one window table are MERGED into one
+// pipeline (msm_run_multi: one sort, one accumulation, one reduction with a bucket set per job -- the fixed ~0.85 ms
+// tail of an MSM is paid once, and the merged list is long enough for the batched-affine rounds); what cannot be merged
+// (no table, different bases, more than MSM_MAX_JOBS) runs as before, group i on lane i & 1 -- lane 1 is the context's
+// auxiliary stream with its own scratch arena -- so that the latency-bound tail of one group overlaps the pipe-bound
+// accumulation of the other.  Every job leaves its affine result in its own 64-byte slot; one D2H copy and one
+// synchronisation fetch them all.
 int msm_run_batch(kzg_ctx* ctx, const MsmJob* jobs, uint32_t count, uint8_t* out_affine) {
     if (count == 0) return KZG_OK;
-    if (count > 30) return set_err(ctx, KZG_ERR_ARG, "at most 30 commitments per batch");
+    if (count > 30) {  // (the result slots hold 30: longer batches go in segments, one synchronisation each)
+        for (uint32_t i = 0; i < count; i += 30) KZG_TRY(msm_run_batch(ctx, jobs + i, count - i < 30 ? count - i : 30, out_affine + 64 * i));
+        return KZG_OK;
+    }
     G1Affine* affine_slots = (G1Affine*)(ctx->dev_small + 4096);    // 30 x 64 B
     G1XYZZ* xyzz_slots = (G1XYZZ*)(ctx->dev_small + 8192);          // 30 x 128 B
+    // groups of consecutive jobs over the same table
+    struct Group { uint32_t first, count; };
+    std::vector<Group> groups;
+    for (uint32_t i = 0; i < count;) {
+        uint32_t len = 1;
+        if (ctx->tuning.merge && jobs[i].bases.table)
+            while (i + len < count && len < MSM_MAX_JOBS && jobs[i + len].bases.table == jobs[i].bases.table &&
+                   jobs[i + len].bases.stride == jobs[i].bases.stride && jobs[i + len].bases.tab_c == jobs[i].bases.tab_c)
+                len++;
+        groups.push_back({i, len});
+        i += len;
+    }
     cudaStream_t main_stream = ctx->stream;
     int r = KZG_OK;
-    const bool two_lanes = count > 1;
+    const bool two_lanes = groups.size() > 1;
     if (two_lanes) {
         // lane 1 may start once everything queued so far on the main stream (the scalars' producers) is done
         KZG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
         KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     }
-    for (uint32_t i = 0; i < count && r == KZG_OK; i++) {
-        const int lane = two_lanes ? (int)(i & 1) : 0;
+    for (size_t gi = 0; gi < groups.size() && r == KZG_OK; gi++) {
+        const Group& gr = groups[gi];
+        const int lane = two_lanes ? (int)(gi & 1) : 0;
         ctx->lane = lane;
         ctx->stream = lane ? ctx->aux_stream : main_stream;
-        r = msm_run(ctx, jobs[i].bases, jobs[i].src, jobs[i].n, xyzz_slots + i);
+        MsmJobs mj;
+        memset(&mj, 0, sizeof(mj));
+        mj.count = gr.count;
+        for (uint32_t j = 0; j < gr.count; j++) {
+            mj.scalars[j] = jobs[gr.first + j].src.scalars;
+            mj.n[j] = jobs[gr.first + j].n;
+            if (jobs[gr.first + j].src.montgomery) mj.montgomery |= 1u << j;
+        }
+        r = msm_run_multi(ctx, jobs[gr.first].bases, mj, xyzz_slots + gr.first);
         if (r == KZG_OK) {
-            KZG_LAUNCH(ctx, g1_finish_kernel, 1, 32, 0, xyzz_slots + i, 1u, affine_slots + i);
+            KZG_LAUNCH(ctx, g1_finish_many_kernel, gr.count, 32, 0, xyzz_slots + gr.first, affine_slots + gr.first);
             if (cudaGetLastError() != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, "g1_finish launch failed");
         }
     }
@@ -1895,6 +2146,7 @@ static MsmBases raw_bases(const G1Affine* pts) {
 extern "C" {
 
 int kzg_msm_geometry(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx) return KZG_ERR_ARG;
     MsmBases b = srs ? srs_bases(ctx, srs, 0) : raw_bases(nullptr);
     MsmGeom g = msm_geometry(ctx, b, n ? n : 1, montgomery != 0);
@@ -1905,15 +2157,17 @@ int kzg_msm_geometry(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uin
 
 int kzg_msm_plan(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows,
                  uint32_t* affine_rounds) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx) return KZG_ERR_ARG;
     MsmBases b = srs ? srs_bases(ctx, srs, 0) : raw_bases(nullptr);
     MsmGeom g = msm_geometry(ctx, b, n ? n : 1, montgomery != 0);
     if (window_bits) *window_bits = g.c;
     if (windows) *windows = g.nwin;
-    if (affine_rounds) *affine_rounds = msm_affine_rounds((n ? n : 1) * g.nwin, g.nsets * g.nbuckets);
+    if (affine_rounds) *affine_rounds = msm_affine_rounds(ctx, (n ? n : 1) * g.nwin, g.nsets * g.nbuckets);
     return KZG_OK;
 }
 int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx) return KZG_ERR_ARG;
     if (c != 0 && (c < 2 || c > 22)) return set_err(ctx, KZG_ERR_ARG, "msm window must be 0 (auto) or in [2, 22]");
     ctx->msm_window = c;
@@ -1921,6 +2175,7 @@ int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c) {
 }
 
 int kzg_srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t window_bits) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !srs) return KZG_ERR_ARG;
     return srs_precompute(ctx, srs, window_bits);
 }
@@ -1928,6 +2183,7 @@ int kzg_srs_precompute(kzg_ctx* ctx, kzg_srs* srs, uint32_t window_bits) {
 // commit(pol): MSM length = min(len, |SRS|); coefficients beyond the SRS must be zero (the reference
 // slices PTau to degree+1 points, polynomial.js:1107-1108 -- trailing zero coefficients never matter).
 int kzg_commit(kzg_ctx* ctx, kzg_srs* srs, kzg_buf* coef, uint8_t out_affine[64]) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !srs || !coef || !out_affine) return KZG_ERR_ARG;
     uint64_t n = coef->n;
     if (n > srs->n) {
@@ -1943,6 +2199,7 @@ int kzg_commit(kzg_ctx* ctx, kzg_srs* srs, kzg_buf* coef, uint8_t out_affine[64]
 }
 
 int kzg_srs_msm(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std, uint64_t n, uint8_t out_affine[64]) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !srs || !scalars_std || !out_affine) return KZG_ERR_ARG;
     if (first + n > srs->n || n > scalars_std->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
     MsmScalarSrc src{scalars_std->d, false};
@@ -1951,6 +2208,7 @@ int kzg_srs_msm(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std
 }
 
 int kzg_srs_msm_partial(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* scalars_std, uint64_t n, void* partial_dev) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !srs || !scalars_std || !partial_dev) return KZG_ERR_ARG;
     if (first + n > srs->n || n > scalars_std->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
     MsmScalarSrc src{scalars_std->d, false};
@@ -1958,6 +2216,7 @@ int kzg_srs_msm_partial(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, kzg_buf* sca
 }
 
 int kzg_g1_partials_combine(kzg_ctx* ctx, const void* partials_dev, uint32_t count, uint8_t out_affine[64]) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !partials_dev || !out_affine || count == 0) return KZG_ERR_ARG;
     return msm_result_to_host_affine(ctx, (const G1XYZZ*)partials_dev, count, out_affine);
 }
@@ -1966,42 +2225,36 @@ int kzg_g1_partials_combine(kzg_ctx* ctx, const void* partials_dev, uint32_t cou
 // Large inputs are cut into growing pieces (1/8, 2/8, 5/8 of the points): all the uploads are queued on the
 // auxiliary stream (copy engine) at once, and the MSM of piece k on the main stream waits only for ITS upload, so that
 // only the first, small upload is exposed and every later one hides behind the previous piece's MSM (each piece's MSM
-// takes longer than the next piece's upload at PCIe 5 x16 rates); the partial points are added by g1_finish.
+// takes longer than the next piece's upload at PCIe 5 x16 rates).  Leaves `*parts_out` partial points in `slots`.
 // (The overlap needs pinned host memory; with pageable memory the call is still correct, just serial.)
-int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
-                     uint8_t out_affine[64]) {
-    if (!ctx || !srs || (!scalars_std_host && n) || !out_affine) return KZG_ERR_ARG;
-    if (first + n > srs->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
+static int srs_msm_host_pieces(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
+                               G1XYZZ* slots, uint32_t* parts_out) {
     Fr* tmp = nullptr;
     if (n) KZG_CUDA(ctx, cudaMallocAsync((void**)&tmp, sizeof(Fr) * n, ctx->stream));
     const Fr* host = (const Fr*)scalars_std_host;
-    G1XYZZ* slots = (G1XYZZ*)(ctx->dev_small + 8192);
     int r = KZG_OK;
     uint32_t parts = 1;
-    if (n >= (1ull << 22)) {
+    if (n >= (1ull << ctx->tuning.host_piece_min_log)) {
         // every piece pays the fixed part of an MSM again (~1.3 ms with 2^19 buckets, ~2.2 ms with the 2^21 buckets of a
         // c = 22 table): three pieces of 1/8, 2/8, 5/8 for the former, two of 3/16, 13/16 for the latter
         uint64_t cut[4] = {0, n / 8, n / 8 + n / 4, n};
         parts = 3;
-        if (srs->table && srs->tab_c > 20 && ctx->msm_window == 0) {
+        if (n < (1ull << 22) || (srs->table && srs->tab_c > 20 && ctx->msm_window == 0)) {
             parts = 2;
             cut[1] = n / 16 * 3;
             cut[2] = n;
-            if (const char* ov = getenv("KZGB200_HOST_PIECES")) {  // tuning: "a,b" = cuts at a/64 and b/64 of n (b = 64: two pieces)
-                int a = 0, b = 64;
-                if (sscanf(ov, "%d,%d", &a, &b) >= 1 && a > 0 && a < b && b <= 64) {
-                    cut[1] = n / 64 * a;
-                    cut[2] = b < 64 ? n / 64 * b : n;
-                    cut[3] = n;
-                    parts = b < 64 ? 3 : 2;
-                }
-            }
+        }
+        if (ctx->tuning.host_cut_a > 0) {  // tuning: cuts at a/64 and b/64 of n (b = 64: two pieces)
+            const int a = ctx->tuning.host_cut_a, b = ctx->tuning.host_cut_b;
+            cut[1] = n / 64 * a;
+            cut[2] = b < 64 ? n / 64 * b : n;
+            cut[3] = n;
+            parts = b < 64 ? 3 : 2;
         }
         // All uploads are queued at once on the copy stream.  Piece k runs on lane k & 1 (own stream, own scratch arena)
         // and waits only for its own upload, so the next piece starts sorting while the latency-bound tail of the
         // previous one (bucket reduction, the inversions of the affine rounds) is still running.
-        cudaEvent_t up[3] = {nullptr, nullptr, nullptr};
-        for (uint32_t k = 0; k < parts; k++) cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming);
+        cudaEvent_t up[3] = {order_event(ctx), order_event(ctx), order_event(ctx)};
         cudaStream_t main_stream = ctx->stream;
         cudaError_t e = cudaEventRecord(ctx->ev_fork, main_stream);  // tmp exists from here on
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0);
@@ -2027,20 +2280,68 @@ int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* sca
         cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
         cudaEventRecord(ctx->ev_join, ctx->aux_stream);
         cudaStreamWaitEvent(main_stream, ctx->ev_join, 0);
-        if (r == KZG_OK) r = msm_result_to_host_affine(ctx, slots, parts, out_affine);
-        else cudaStreamSynchronize(main_stream);
-        for (uint32_t k = 0; k < parts; k++) cudaEventDestroy(up[k]);
+        if (r != KZG_OK) cudaStreamSynchronize(main_stream);
     } else {
         if (n) KZG_CUDA(ctx, cudaMemcpyAsync(tmp, host, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
         r = msm_run(ctx, srs_bases(ctx, srs, first), MsmScalarSrc{tmp, false}, n, slots);
-        if (r == KZG_OK) r = msm_result_to_host_affine(ctx, slots, parts, out_affine);
     }
     if (tmp) cudaFreeAsync(tmp, ctx->stream);
+    *parts_out = parts;
     return r;
+}
+
+int kzg_srs_msm_host(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
+                     uint8_t out_affine[64]) {
+    kzg::DeviceGuard _dg(ctx);
+    if (!ctx || !srs || (!scalars_std_host && n) || !out_affine) return KZG_ERR_ARG;
+    if (first + n > srs->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
+    G1XYZZ* slots = (G1XYZZ*)(ctx->dev_small + 8192);
+    uint32_t parts = 1;
+    KZG_TRY(srs_msm_host_pieces(ctx, srs, first, scalars_std_host, n, slots, &parts));
+    return msm_result_to_host_affine(ctx, slots, parts, out_affine);
+}
+
+// the multi-GPU form of the same: the rank's shard of the scalars comes from HOST memory (piecewise upload hidden
+// behind the pieces' MSMs) and the shard's sum is left as ONE XYZZ partial in device memory for the all-gather
+int kzg_srs_msm_host_partial(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const void* scalars_std_host, uint64_t n,
+                             void* partial_dev) {
+    kzg::DeviceGuard _dg(ctx);
+    if (!ctx || !srs || (!scalars_std_host && n) || !partial_dev) return KZG_ERR_ARG;
+    if (first + n > srs->n) return set_err(ctx, KZG_ERR_ARG, "msm: slice out of bounds");
+    G1XYZZ* slots = (G1XYZZ*)(ctx->dev_small + 8192);
+    uint32_t parts = 1;
+    KZG_TRY(srs_msm_host_pieces(ctx, srs, first, scalars_std_host, n, slots, &parts));
+    KZG_LAUNCH(ctx, g1_sum_kernel, 1, 32, 0, slots, parts, (G1XYZZ*)partial_dev);
+    KZG_CHECK_LAUNCH(ctx);
+    return KZG_OK;
+}
+
+// commit(pol) for several polynomials over one SRS in one pipeline (multi-MSM over shared bases; the
+// prover's [F],[T] of round 1 and [W_xi],[W_xiw] of round 5, prover.js:161-162,409-410).  out_affine: 64 B per polynomial.
+int kzg_commit_many(kzg_ctx* ctx, kzg_srs* srs, kzg_buf* const* coefs, uint32_t count, uint8_t* out_affine) {
+    kzg::DeviceGuard _dg(ctx);
+    if (!ctx || !srs || (!coefs && count) || (!out_affine && count)) return KZG_ERR_ARG;
+    std::vector<MsmJob> jobs(count);
+    for (uint32_t i = 0; i < count; i++) {
+        if (!coefs[i]) return KZG_ERR_ARG;
+        uint64_t n = coefs[i]->n;
+        if (n > srs->n) {
+            uint64_t deg = 0;
+            KZG_TRY(poly_degree(ctx, coefs[i]->d, coefs[i]->n, &deg));
+            if (deg + 1 > srs->n)
+                return set_err(ctx, KZG_ERR_PROTOCOL, "The Powers of Tau file is not sufficiently large to commit the polynomials.");
+            n = srs->n;
+        }
+        jobs[i].bases = srs_bases(ctx, srs, 0);
+        jobs[i].src = MsmScalarSrc{coefs[i]->d, true};
+        jobs[i].n = n;
+    }
+    return msm_run_batch(ctx, jobs.data(), count, out_affine);
 }
 
 int kzg_g1_msm_affine(kzg_ctx* ctx, const void* bases, const void* scalars_std, uint64_t n, uint32_t flags,
                       uint8_t out_affine[64], uint8_t out_jacobian[96]) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || (!bases && n) || (!scalars_std && n) || !out_affine) return KZG_ERR_ARG;
     const G1Affine* d_bases = (const G1Affine*)bases;
     const Fr* d_scalars = (const Fr*)scalars_std;

@@ -176,12 +176,17 @@ static uint32_t log2u(uint64_t n) {
 extern "C" {
 
 uint32_t kzg_prover_n_evals(kzg_prover* p) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p) return 0;
     return (p->kind == KZG_GRANDSUM ? 2 * p->k : p->k) + (p->selected ? 2 : 0) + 1;
 }
-uint32_t kzg_prover_n_round1_commitments(kzg_prover* p) { return p ? 2 * p->k + (p->selected ? 2 : 0) : 0; }
+uint32_t kzg_prover_n_round1_commitments(kzg_prover* p) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
+    return p ? 2 * p->k + (p->selected ? 2 : 0) : 0;
+}
 
 int kzg_prover_take_evals(kzg_prover* p, uint32_t column, int which, kzg_buf** out) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p || !out || column >= p->k || (which != 0 && which != 1)) return KZG_ERR_ARG;
     kzg_ctx* ctx = p->ctx;
     if (p->round < 5) return set_err(ctx, KZG_ERR_ARG, "evaluations can be taken after round 5 only");
@@ -201,6 +206,7 @@ int kzg_prover_take_evals(kzg_prover* p, uint32_t column, int which, kzg_buf** o
 }
 
 int kzg_prover_destroy(kzg_prover* p) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p) return KZG_OK;
     if (p->cos_queued) cudaStreamWaitEvent(p->ctx->stream, p->cos_ready, 0);  // lane 1 may still be writing p->cos
     if (p->cos) cudaFreeAsync(p->cos, p->ctx->stream);
@@ -211,11 +217,11 @@ int kzg_prover_destroy(kzg_prover* p) {
 }
 
 int kzg_prover_create(kzg_ctx* ctx, kzg_srs* srs, int kind, uint32_t n_bits, uint32_t n_pols, int selected, kzg_prover** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !srs || !out) return KZG_ERR_ARG;
     if (kind != KZG_GRANDSUM && kind != KZG_GRANDPRODUCT) return set_err(ctx, KZG_ERR_ARG, "unknown argument kind");
     if (n_pols == 0) return set_err(ctx, KZG_ERR_PROTOCOL, "The number of multisets must be greater than 0.");
     if (n_bits < 1 || n_bits > 24) return set_err(ctx, KZG_ERR_ARG, "n_bits must be in [1, 24]");
-    if (2 * n_pols + 6 > 28) return set_err(ctx, KZG_ERR_ARG, "at most 11 columns per argument");
     const uint64_t n = 1ull << n_bits;
     // the reference needs a ptau of power >= nBits (prover.js:79-81), i.e. 2n - 1 points
     if (srs->n < 2 * n - 1)
@@ -332,6 +338,7 @@ static int coset_prefetch(kzg_prover* p) {
 
 int kzg_prover_round1(kzg_prover* p, const uint8_t* const* evals_f_std, const uint8_t* const* evals_t_std,
                       const uint8_t* sel_f, const uint8_t* sel_t, uint8_t* commitments_out) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p || !evals_f_std || !evals_t_std || !commitments_out) return KZG_ERR_ARG;
     kzg_ctx* ctx = p->ctx;
     if (p->selected && (!sel_f || !sel_t)) return set_err(ctx, KZG_ERR_ARG, "selected prover needs both selector columns");
@@ -371,6 +378,7 @@ int kzg_prover_round1(kzg_prover* p, const uint8_t* const* evals_f_std, const ui
 
 // ---- round 2 -----------------------------------------------------------------------------------------
 int kzg_prover_round2(kzg_prover* p, const uint8_t beta[32], const uint8_t gamma[32], uint8_t out_acc[64]) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p || !gamma || !out_acc) return KZG_ERR_ARG;
     kzg_ctx* ctx = p->ctx;
     if (p->round < 1) return set_err(ctx, KZG_ERR_ARG, "prover rounds must run in order");
@@ -409,6 +417,7 @@ int kzg_prover_round2(kzg_prover* p, const uint8_t beta[32], const uint8_t gamma
 
 // ---- round 3 -----------------------------------------------------------------------------------------
 int kzg_prover_round3(kzg_prover* p, const uint8_t alpha[32], uint8_t out_q[64]) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p || !alpha || !out_q) return KZG_ERR_ARG;
     kzg_ctx* ctx = p->ctx;
     if (p->round < 2) return set_err(ctx, KZG_ERR_ARG, "prover rounds must run in order");
@@ -484,6 +493,7 @@ int kzg_prover_round3(kzg_prover* p, const uint8_t alpha[32], uint8_t out_q[64])
 
 // ---- round 4 -----------------------------------------------------------------------------------------
 int kzg_prover_round4(kzg_prover* p, const uint8_t xi[32], uint8_t* evals_out) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p || !xi || !evals_out) return KZG_ERR_ARG;
     kzg_ctx* ctx = p->ctx;
     if (p->round < 3) return set_err(ctx, KZG_ERR_ARG, "prover rounds must run in order");
@@ -518,6 +528,7 @@ int kzg_prover_round4(kzg_prover* p, const uint8_t xi[32], uint8_t* evals_out) {
 
 // ---- round 5 -----------------------------------------------------------------------------------------
 int kzg_prover_round5(kzg_prover* p, const uint8_t v_bytes[32], uint8_t out_w[128]) {
+    kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p || !v_bytes || !out_w) return KZG_ERR_ARG;
     kzg_ctx* ctx = p->ctx;
     if (p->round < 4) return set_err(ctx, KZG_ERR_ARG, "prover rounds must run in order");

@@ -114,6 +114,7 @@ using namespace kzg;
 extern "C" {
 
 int kzg_ptau_read_header(kzg_ctx* ctx, const char* path, uint32_t* power, uint32_t* ceremony_power) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !path || !power || !ceremony_power) return KZG_ERR_ARG;
     FILE* f = fopen(path, "rb");
     if (!f) return set_err(ctx, KZG_ERR_IO, std::string(path) + ": cannot open");
@@ -125,6 +126,7 @@ int kzg_ptau_read_header(kzg_ctx* ctx, const char* path, uint32_t* power, uint32
 }
 
 int kzg_ptau_read_tau_g2(kzg_ctx* ctx, const char* path, uint8_t out[128]) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !path || !out) return KZG_ERR_ARG;
     FILE* f = fopen(path, "rb");
     if (!f) return set_err(ctx, KZG_ERR_IO, std::string(path) + ": cannot open");
@@ -142,6 +144,7 @@ int kzg_ptau_read_tau_g2(kzg_ctx* ctx, const char* path, uint8_t out[128]) {
 }
 
 int kzg_srs_from_host(kzg_ctx* ctx, const uint8_t* affine, uint64_t n_points, kzg_srs** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !out || (!affine && n_points)) return KZG_ERR_ARG;
     kzg_srs* s = new kzg_srs();
     s->n = n_points;
@@ -164,6 +167,7 @@ int kzg_srs_from_host(kzg_ctx* ctx, const uint8_t* affine, uint64_t n_points, kz
 }
 
 int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs** out, uint32_t* power_out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !path || !out) return KZG_ERR_ARG;
     FILE* f = fopen(path, "rb");
     if (!f) return set_err(ctx, KZG_ERR_IO, std::string(path) + ": cannot open");
@@ -194,10 +198,12 @@ int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs
 }
 
 int kzg_srs_generate(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t n_points, kzg_srs** out) {
+    kzg::DeviceGuard _dg(ctx);
     return kzg_srs_generate_range(ctx, tau_std, 0, n_points, out);
 }
 
 int kzg_srs_generate_range(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t first, uint64_t n_points, kzg_srs** out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !tau_std || !out) return KZG_ERR_ARG;
     kzg_srs* s = new kzg_srs();
     s->n = n_points;
@@ -236,6 +242,7 @@ int kzg_srs_generate_range(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t fir
 }
 
 int kzg_srs_download(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, uint64_t count, uint8_t* out) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !srs || (!out && count)) return KZG_ERR_ARG;
     if (first + count > srs->n) return set_err(ctx, KZG_ERR_ARG, "SRS download out of bounds");
     if (!count) return KZG_OK;
@@ -246,6 +253,7 @@ int kzg_srs_download(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, uint64_t count,
 
 int kzg_srs_write_ptau(kzg_ctx* ctx, kzg_srs* srs, uint32_t power, const uint8_t g2_one[128], const uint8_t g2_tau[128],
                        const char* path) {
+    kzg::DeviceGuard _dg(ctx);
     if (!ctx || !srs || !g2_one || !g2_tau || !path) return KZG_ERR_ARG;
     std::vector<uint8_t> pts((size_t)srs->n * 64);
     KZG_TRY(kzg_srs_download(ctx, srs, 0, srs->n, pts.data()));
@@ -279,6 +287,7 @@ uint64_t kzg_srs_len(kzg_srs* srs) { return srs ? srs->n : 0; }
 void* kzg_srs_device_ptr(kzg_srs* srs) { return srs ? (void*)srs->d : nullptr; }
 
 int kzg_srs_free(kzg_ctx* ctx, kzg_srs* srs) {
+    kzg::DeviceGuard _dg(ctx);
     if (!srs) return KZG_OK;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     cudaFree(srs->d);

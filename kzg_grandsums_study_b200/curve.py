@@ -271,6 +271,10 @@ class Curve(HostCurve):
     def launch_count(self):
         return int(self.lib.kzg_ctx_launch_count(self.ctx))
 
+    def set_option(self, name, value):
+        """MSM tuning knob (kzg_ctx_set_option): A/B timing and the forced paths of the tests; value < 0 = default"""
+        self.check(self.lib.kzg_ctx_set_option(self.ctx, name.encode(), int(value)))
+
     def _convert(self, buf, to_mont):
         d = self.to_device(buf)
         out = self.alloc(d.length(), zero=False)
@@ -289,22 +293,32 @@ class Curve(HostCurve):
 
     # ---- SRS ----------------------------------------------------------------------------------------
     def load_srs(self, ptau_path, n_points):
-        """device-resident [tau^i]_1 from a .ptau file (prover.js:15-16,83-85); cached per (path, size)"""
-        key = (os.path.abspath(ptau_path), int(n_points))
-        if key not in self._srs_cache:
+        """device-resident [tau^i]_1 from a .ptau file (prover.js:15-16,83-85).  Cached per (path, size AND the file's
+        identity: mtime, byte size) -- a .ptau rewritten in place with another tau is loaded afresh, the stale device
+        copy (and its window table) is released."""
+        path = os.path.abspath(ptau_path)
+        st = os.stat(path)
+        key = (path, int(n_points))
+        ident = (st.st_mtime_ns, st.st_size)
+        hit = self._srs_cache.get(key)
+        if hit is not None and hit[2] != ident:
+            self.lib.kzg_srs_free(self.ctx, hit[0])
+            del self._srs_cache[key]
+            hit = None
+        if hit is None:
             h = C.c_void_p()
             power = C.c_uint32()
             self.check(self.lib.kzg_srs_load_ptau(self.ctx, ptau_path.encode(), n_points, C.byref(h), C.byref(power)))
             if os.environ.get("KZGB200_NO_SRS_TABLE") != "1":
                 c = int(os.environ.get("KZGB200_TABLE_WINDOW", "0"))        # 0 = the library's cost model
                 self.check(self.lib.kzg_srs_precompute(self.ctx, h, c))   # one-off window table (msm.cu)
-            self._srs_cache[key] = (h, power.value)
-        return self._srs_cache[key]
+            hit = self._srs_cache[key] = (h, power.value, ident)
+        return hit[0], hit[1]
 
     def terminate(self):
         if self.ctx:
-            for h, _ in self._srs_cache.values():
-                self.lib.kzg_srs_free(self.ctx, h)
+            for entry in self._srs_cache.values():
+                self.lib.kzg_srs_free(self.ctx, entry[0])
             self._srs_cache = {}
             self.lib.kzg_ctx_destroy(self.ctx)
             self.ctx = None

@@ -41,6 +41,14 @@ def g1_from_bytes(b):
     return (fq_from_mont(b[:32]), fq_from_mont(b[32:]))
 
 
+def g1_bytes_canonical(b):
+    """both coordinates are reduced residues (raw little-endian integer < q).  A coordinate + q decodes to the same
+    point but hashes differently in the transcript (G1.toRprUncompressed works on the raw bytes), so the verifiers
+    refuse such encodings before the Montgomery conversion makes the difference invisible."""
+    b = bytes(b)
+    return len(b) == 64 and int.from_bytes(b[:32], "little") < Q and int.from_bytes(b[32:], "little") < Q
+
+
 def g1_to_bytes(P):
     return bytes(64) if P is None else fq_to_mont(P[0]) + fq_to_mont(P[1])
 

@@ -35,10 +35,15 @@ class ShardedSrsMsm:
         self.partial_fn = partial_fn or self._partial_device
         self.combine_fn = combine_fn or self._combine_device
 
-    def _partial_device(self, scalars_handle, count, out):
+    def _partial_device(self, scalars, count, out):
+        """`scalars`: a device buffer handle (resident shard) or a HOST buffer / tensor (end-to-end: the upload is
+        inside, piecewise, hidden behind the pieces' MSMs)"""
         from ._lib import as_ptr
         c = self.curve
-        c.check(c.lib.kzg_srs_msm_partial(c.ctx, self.srs, 0, scalars_handle, count, as_ptr(out)))
+        if isinstance(scalars, C.c_void_p) or isinstance(scalars, int):
+            c.check(c.lib.kzg_srs_msm_partial(c.ctx, self.srs, 0, scalars, count, as_ptr(out)))
+        else:
+            c.check(c.lib.kzg_srs_msm_host_partial(c.ctx, self.srs, 0, as_ptr(scalars), count, as_ptr(out)))
 
     def _combine_device(self, gathered, world):
         from ._lib import as_ptr
@@ -47,12 +52,26 @@ class ShardedSrsMsm:
         c.check(c.lib.kzg_g1_partials_combine(c.ctx, as_ptr(gathered), world, as_ptr(out)))
         return bytes(out)
 
-    def msm(self, scalars_handle, count):
-        """scalars: this rank's shard (device buffer handle, standard-form LE); returns the 64-byte affine sum over
-        ALL ranks' shards (identical on every rank)"""
-        self.partial_fn(scalars_handle, count, self.partial)
+    def _torch_stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def msm(self, scalars, count):
+        """scalars: this rank's shard (device buffer handle or host buffer, standard-form LE); returns the 64-byte
+        affine sum over ALL ranks' shards (identical on every rank).
+
+        Three steps on two streams: the shard's MSM on the library context's stream, the all-gather on torch's current
+        stream (NCCL orders itself against it), the combine on the context's stream again.  The order is made explicit
+        with one event each way (kzg_stream_wait_ctx / kzg_ctx_wait_stream) -- a context on a private stream would
+        otherwise let the collective read a partial that is still being computed."""
+        self.partial_fn(scalars, count, self.partial)
         if self.world == 1:
             return self.combine_fn(self.partial, 1)
         import torch.distributed as dist
+        on_device = self.curve is not None and self.partial.is_cuda
+        if on_device:
+            c = self.curve
+            c.check(c.lib.kzg_stream_wait_ctx(c.ctx, self._torch_stream()))   # gather after the partial is complete
         dist.all_gather_into_tensor(self.gathered, self.partial, group=self.group)
+        if on_device:
+            c.check(c.lib.kzg_ctx_wait_stream(c.ctx, self._torch_stream()))   # combine after the gather has landed
         return self.combine_fn(self.gathered, self.world)

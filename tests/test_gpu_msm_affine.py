@@ -42,7 +42,7 @@ def test_affine_rounds_vs_closed_form(curve, tau, flavour, c, rounds, monkeypatc
                  [0] * n,                                   # no entries at all
                  [R - 1 - (i % 2) for i in range(n)],
                  [(i % 7) + 1 for i in range(n)]]           # seven buckets, odd and even sizes
-        monkeypatch.setenv("KZGB200_AFF_ROUNDS", rounds)
+        curve.set_option("aff_rounds", int(rounds))
         for scalars in cases:
             expect = sum(s * pow(tau, i, R) for i, s in enumerate(scalars)) % R
             want = bn.g1_to_bytes(bn.g1_mul_gen(expect))
@@ -52,7 +52,7 @@ def test_affine_rounds_vs_closed_form(curve, tau, flavour, c, rounds, monkeypatc
             curve.check(curve.lib.kzg_commit(curve.ctx, srs, mont.handle, as_ptr(out)))
             assert bytes(out) == want, (flavour, c, rounds, "commit")
     finally:
-        monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+        curve.set_option("aff_rounds", -1)
         curve.check(curve.lib.kzg_msm_set_window(curve.ctx, 0))
         curve.lib.kzg_srs_free(curve.ctx, srs)
 
@@ -76,13 +76,13 @@ def test_affine_rounds_exceptional_pairs(curve, rounds, monkeypatch):
         try:
             for table_c in (0, 5):
                 curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, table_c))
-                monkeypatch.setenv("KZGB200_AFF_ROUNDS", rounds)
+                curve.set_option("aff_rounds", int(rounds))
                 for scalars in ([7] * n, inputs.random_column(3, n), [R - 1] * n, [(i % 5) + 1 for i in range(n)]):
                     expect = sum(s * c for s, c in zip(scalars, coeffs)) % R
                     assert _srs_msm(curve, srs, scalars, n) == bn.g1_to_bytes(bn.g1_mul_gen(expect)), (table_c, scalars[0])
-                monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+                curve.set_option("aff_rounds", -1)
         finally:
-            monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+            curve.set_option("aff_rounds", -1)
             curve.lib.kzg_srs_free(curve.ctx, srs)
 
 
@@ -103,20 +103,20 @@ def test_affine_rounds_match_the_xyzz_walk(curve, tau, log_n, monkeypatch):
         got = {}
         for rounds in ("0", "2", "4", None):
             if rounds is None:
-                monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+                curve.set_option("aff_rounds", -1)
             else:
-                monkeypatch.setenv("KZGB200_AFF_ROUNDS", rounds)
+                curve.set_option("aff_rounds", int(rounds))
             got[rounds] = p.multiExponentiation(srs)
         assert all(v == want for v in got.values()), {k: v == want for k, v in got.items()}
     finally:
-        monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+        curve.set_option("aff_rounds", -1)
         curve.lib.kzg_srs_free(curve.ctx, srs)
 
 
 def test_msm_plan_reports_the_rounds(curve, monkeypatch):
     """kzg_msm_plan: what an n-point MSM will do -- no rounds for small inputs, some for 2^24 points, and the override"""
     c, w, r = C.c_uint32(), C.c_uint32(), C.c_uint32()
-    monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+    curve.set_option("aff_rounds", -1)
     for n, want in ((1, 0), (1 << 16, 0), (1 << 20, 0)):
         curve.check(curve.lib.kzg_msm_plan(curve.ctx, None, n, 0, C.byref(c), C.byref(w), C.byref(r)))
         assert r.value == want and w.value == -(-257 // c.value), (n, c.value, w.value, r.value)
@@ -125,10 +125,10 @@ def test_msm_plan_reports_the_rounds(curve, monkeypatch):
     g_c, g_w = C.c_uint32(), C.c_uint32()
     curve.check(curve.lib.kzg_msm_geometry(curve.ctx, None, 1 << 24, 0, C.byref(g_c), C.byref(g_w)))
     assert (g_c.value, g_w.value) == (c.value, w.value)
-    monkeypatch.setenv("KZGB200_AFF_ROUNDS", "2")
+    curve.set_option("aff_rounds", 2)
     curve.check(curve.lib.kzg_msm_plan(curve.ctx, None, 1000, 1, C.byref(c), C.byref(w), C.byref(r)))
     assert r.value == 2 and w.value == -(-255 // c.value)
-    monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+    curve.set_option("aff_rounds", -1)
 
 
 @pytest.mark.parametrize("kind", ["gs", "gp"])
@@ -149,11 +149,11 @@ def test_whole_proofs_with_forced_rounds(kind, rounds, curve, tau, ptau_factory,
     gpu = mset_eq_kzg_grandsum_prover if kind == "gs" else mset_eq_kzg_grandproduct_prover
     cpu = pr.grandsum_prover if kind == "gs" else pr.grandproduct_prover
     want = cpu(pr.TrapdoorSrs(tau, nbits), [fb], [tb])
-    monkeypatch.setenv("KZGB200_AFF_ROUNDS", rounds)
+    curve.set_option("aff_rounds", int(rounds))
     try:
         got = gpu(path, Evaluations(fb, curve), Evaluations(tb, curve))
     finally:
-        monkeypatch.delenv("KZGB200_AFF_ROUNDS", raising=False)
+        curve.set_option("aff_rounds", -1)
     assert pr.proof_bytes(got) == pr.proof_bytes(want)
 
 

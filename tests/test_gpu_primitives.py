@@ -410,7 +410,7 @@ def test_msm_reduction_geometries(curve, tau, table_c, monkeypatch):
                  [(i % 3) + 1 for i in range(n)],                       # three buckets hold everything
                  [((1 << table_c) - 1) << (table_c * (i % 5)) for i in range(n)]]  # top digits: carries into the next window
         for k0 in ("0", "1", "2", "3", "5"):
-            monkeypatch.setenv("KZGB200_RED_K0", k0)
+            curve.set_option("red_k0", int(k0))
             for scalars in cases:
                 expect = sum(s * pow(tau, i, R) for i, s in enumerate(scalars)) % R
                 buf = curve.to_device(bn.fr_vec_to_std_bytes(scalars))
@@ -418,7 +418,7 @@ def test_msm_reduction_geometries(curve, tau, table_c, monkeypatch):
                 curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out)))
                 assert bytes(out) == bn.g1_to_bytes(bn.g1_mul_gen(expect)), (table_c, k0)
     finally:
-        monkeypatch.delenv("KZGB200_RED_K0", raising=False)
+        curve.set_option("red_k0", -1)
         curve.lib.kzg_srs_free(curve.ctx, srs)
 
 
@@ -441,7 +441,7 @@ def test_msm_partition_sort(curve, tau, flavour, c, monkeypatch):
         cases = [[sum(int(scal[i, j]) << (64 * j) for j in range(4)) for i in range(n)],
                  [5] * n, [0] * n, [R - 1 - (i % 2) for i in range(n)]]
         for part_sort in ("1", "0"):
-            monkeypatch.setenv("KZGB200_PART_SORT", part_sort)
+            curve.set_option("part_sort", int(part_sort))
             for scalars in cases:
                 expect = sum(s * pow(tau, i, R) for i, s in enumerate(scalars)) % R
                 want = bn.g1_to_bytes(bn.g1_mul_gen(expect))
@@ -454,7 +454,7 @@ def test_msm_partition_sort(curve, tau, flavour, c, monkeypatch):
                 curve.check(curve.lib.kzg_commit(curve.ctx, srs, mont.handle, as_ptr(out)))
                 assert bytes(out) == want, (flavour, c, part_sort, "commit")
     finally:
-        monkeypatch.delenv("KZGB200_PART_SORT", raising=False)
+        curve.set_option("part_sort", -1)
         curve.check(curve.lib.kzg_msm_set_window(curve.ctx, 0))
         curve.lib.kzg_srs_free(curve.ctx, srs)
 
@@ -469,7 +469,7 @@ def test_msm_huge_buckets(curve, tau, part_sort, monkeypatch):
     curve.check(curve.lib.kzg_srs_generate(curve.ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(srs)))
     try:
         curve.check(curve.lib.kzg_srs_precompute(curve.ctx, srs, 12))
-        monkeypatch.setenv("KZGB200_PART_SORT", part_sort)
+        curve.set_option("part_sort", int(part_sort))
         rnd = inputs.random_column(77, n)
         scalars = [3 if i < 6000 else (5 << 12) if i < 6600 else rnd[i] for i in range(n)]
         expect = sum(s * pow(tau, i, R) for i, s in enumerate(scalars)) % R
@@ -478,5 +478,5 @@ def test_msm_huge_buckets(curve, tau, part_sort, monkeypatch):
         curve.check(curve.lib.kzg_srs_msm(curve.ctx, srs, 0, buf.handle, n, as_ptr(out)))
         assert bytes(out) == bn.g1_to_bytes(bn.g1_mul_gen(expect))
     finally:
-        monkeypatch.delenv("KZGB200_PART_SORT", raising=False)
+        curve.set_option("part_sort", -1)
         curve.lib.kzg_srs_free(curve.ctx, srs)

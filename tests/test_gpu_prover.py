@@ -324,18 +324,17 @@ def test_degenerate_columns(kind, curve, tau, ptau_factory):
     assert zero["commitments"]["F"] == bytes(64) and zero["commitments"]["T"] == bytes(64)
 
 
-def test_column_count_limits(curve, tau, ptau_factory):
-    """k = 11 columns work; more are refused with a clear message (the fused linear combinations take 28 terms)"""
-    from kzg_grandsums_study_b200 import KzgError
+def test_many_columns(curve, tau, ptau_factory):
+    """the reference accepts any number of columns (prover.js:34-45): k = 11 (one fused linear combination), k = 16
+    (34 opening terms: the combinations go in chunks of 28, 32 round-1 commitments go in two result batches) and, for
+    the grand product, k = 30"""
     n = 8
-    cols_f = [inputs.random_column(500 + i, n) for i in range(11)]
-    cols_t = [inputs.rotate_right(c) for c in cols_f]
-    got, want = _prove_pair("gs", curve, tau, ptau_factory, 3, cols_f, cols_t)
-    assert pr.proof_bytes(got) == pr.proof_bytes(want)
-    cols_f.append(inputs.random_column(999, n))
-    cols_t.append(inputs.rotate_right(cols_f[-1]))
-    with pytest.raises(KzgError, match="at most 11 columns"):
-        _prove_pair("gs", curve, tau, ptau_factory, 3, cols_f, cols_t)
+    for kind, k in (("gs", 11), ("gs", 16), ("gp", 30)):
+        cols_f = [inputs.random_column(500 + i, n) for i in range(k)]
+        cols_t = [inputs.rotate_right(c) for c in cols_f]
+        got, want = _prove_pair(kind, curve, tau, ptau_factory, 3, cols_f, cols_t)
+        assert pr.proof_bytes(got) == pr.proof_bytes(want), (kind, k)
+        assert list(got["commitments"]) == list(want["commitments"])
 
 
 def test_prover_replaces_evals_by_montgomery_form(curve, tau, ptau_factory):

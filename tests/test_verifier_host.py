@@ -64,3 +64,29 @@ def test_verifiers_accept_and_reject(kind, k, selected, tmp_path, lib_path):
     assert verifier(path, proof, nbits) is True
     # wrong domain size
     assert verifier(path, proof, nbits + 1) is False
+    # a non-canonical encoding of a good commitment (x + q when it fits 256 bits) and a selected proof that lost its
+    # selector evaluations: both refused without raising
+    raw = proof["commitments"]["Q"]
+    x = int.from_bytes(raw[:32], "little")
+    if x + bn.Q < 1 << 256:
+        proof["commitments"]["Q"] = (x + bn.Q).to_bytes(32, "little") + raw[32:]
+        assert verifier(path, proof, nbits) is False
+        proof["commitments"]["Q"] = raw
+    if selected:
+        lost = proof["evaluations"].pop("selFxi")
+        assert verifier(path, proof, nbits) is False
+        proof["evaluations"]["selFxi"] = lost
+
+
+def test_verifier_refuses_non_canonical_and_incomplete_proofs():
+    """a coordinate encoded as x + q names the same point but hashes differently -- refused; a selected proof
+    without selFxi / selTxi is refused, not a KeyError"""
+    from kzg_grandsums_study_b200 import host_bn254 as hb
+    g = hb.g1_to_bytes((1, 2))
+    assert hb.g1_bytes_canonical(g) and hb.g1_bytes_canonical(bytes(64))
+    x = int.from_bytes(g[:32], "little")
+    if x + hb.Q < 1 << 256:
+        shifted = (x + hb.Q).to_bytes(32, "little") + g[32:]
+        assert hb.g1_from_bytes(shifted) == hb.g1_from_bytes(g)
+        assert not hb.g1_bytes_canonical(shifted)
+    assert not hb.g1_bytes_canonical(b"\xff" * 64)

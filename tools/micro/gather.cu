@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 enum { V_LDG = 0, V_CG, V_CS, V_LU, V_CV, V_NOALLOC, V_EVICT_FIRST, V_L2_64, V_L2_128, V_L2_256, V_V8, V_V8_EF, V_COUNT };
 static const char* NAMES[V_COUNT] = {"ld.global.nc (__ldg)",      "ld.global.cg",          "ld.global.cs",
@@ -148,7 +149,30 @@ static void both(const uint4* table, uint64_t records, uint32_t* out) {
     run<V, 64>(table, records, out);
 }
 
+// `gather sweep`: the working-set curve -- is the ~44 G sectors/s of the 12 GiB table a TLB / page-locality limit (then it
+// rises for small tables) or a sector-rate limit of the L2 / DRAM path (then it is flat once the table exceeds the L2)?
+static int sweep() {
+    const double sizes_gib[] = {0.0625, 0.125, 0.25, 0.5, 1, 2, 4, 8, 12, 16, 24, 32};
+    uint32_t* out = nullptr;
+    cudaMalloc(&out, 4);
+    for (double g : sizes_gib) {
+        const uint64_t bytes = (uint64_t)(g * (double)(1ull << 30)), records = bytes / 64;
+        uint4* table = nullptr;
+        if (cudaMalloc(&table, bytes) != cudaSuccess) {
+            printf("allocation of %.3f GiB failed\n", g);
+            return 1;
+        }
+        cudaMemset(table, 1, bytes);
+        printf("== table %.4f GiB\n", g);
+        both<V_LDG>(table, records, out);
+        both<V_L2_64>(table, records, out);
+        cudaFree(table);
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "sweep")) return sweep();
     const uint64_t gib = argc > 1 ? strtoull(argv[1], nullptr, 10) : 8;
     const uint64_t bytes = gib << 30, records = bytes / 64;
     uint4* table = nullptr;
