@@ -31,7 +31,21 @@ TAU_SEED = 1001
 SCALAR_SEED = 6
 PROVE_SEED = 4           # config C4
 MACS_PER_POINT_WINDOW = 10 * 136   # XYZZ mixed add = 8M + 2S = 10 modmul x 136 limb-MACs
-NCU_TRAFFIC_2_24 = 7.974e10            # DRAM bytes (read + write) of one bucket accumulation at 2^24 points: ncu, profiles/r01_msm24_launches.md
+
+
+def ncu_counted(key, family):
+    """profiles/traffic.json (written by tools/summarize_profiles.py from an ncu capture): DRAM bytes and executed wide
+    MACs of the named kernel group -- only while the kernel sources still hash to what was profiled, else None"""
+    from kzg_grandsums_study_b200 import build as b
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        entry = json.load(open(path)).get(key)
+    except Exception:
+        return None
+    if not entry:
+        return None
+    now = b.source_digest(b.MSM_SOURCES if family == "msm" else b.NTT_SOURCES)
+    return entry if entry.get("src_sha16") == now else None
 
 
 def parse_args():
@@ -47,6 +61,8 @@ def parse_args():
     ap.add_argument("--table-window", type=int, default=0, help="window bits of the SRS table (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-log-n", type=int, default=0, help="MSM size of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 2^16..2^24 sweep lines (raw and table MSM)")
+    ap.add_argument("--prove-log-n2", type=int, default=22, help="second prove size reported under prove.also (0 = skip)")
     return ap.parse_args()
 
 
@@ -124,26 +140,54 @@ def cpu_msm_sample(log_n, threads=None):
 
 
 def run_reference(args):
+    """CPU arm: the oracle's C restatement of the reference's multiExpAffine (ffjavascript's unsigned-window Pippenger
+    with its pTSizes table) on ALL host cores.  The real reference (ffjavascript WASM under Node) cannot run on this
+    image; bench/ref_node/time_msm.js is the same measurement for a machine that has Node.
+    Same configuration as the GPU arm whenever the box finishes it in a few minutes: the FULL 2^log_n MSM per step
+    (~5-10 s on 16-32 cores); otherwise a smaller sample, named in `config`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import ctypes as C2
     from oracle.c import binding as ob
+    from oracle.py import inputs
+    from kzg_grandsums_study_b200 import synthetic
     cores = os.cpu_count() or 1
-    # bounded sample of the same workload: 2^20 of the 2^24 (point, scalar) pairs per step
-    sample_log = args.cpu_sample_log_n or min(args.log_n, 20)
-    for _ in range(max(args.warmup, 0) and 1):
-        ob.bench_msm(sample_log, TAU_SEED, SCALAR_SEED, cores)
+    budget_s = 200.0
+    sample_log = args.cpu_sample_log_n or args.log_n
+    lib = ob.lib()
+    tau = inputs.tau_from_seed(TAU_SEED)
+    # a quick 2^18 probe sizes the run: the full size only if K + W steps (and the SRS generation) fit the budget
+    mpts_probe, _, _ = ob.bench_msm(18, TAU_SEED, SCALAR_SEED, cores)
+    steps_total = args.steps + (1 if args.warmup > 0 else 0)
+    if not args.cpu_sample_log_n:
+        while sample_log > 18 and ((1 << sample_log) / (mpts_probe * 1e6)) * (steps_total + 1.5) > budget_s:
+            sample_log -= 2
+    n = 1 << sample_log
+    bases = C2.create_string_buffer(64 * n)
+    lib.ko_srs_generate(ob._buf(int(tau).to_bytes(32, "little")), 0, n, bases, cores)
+    scal = ob._buf(synthetic.random_fr_std(SCALAR_SEED, 1 << args.log_n)[:n].tobytes())
+    out = C2.create_string_buffer(64)
     times = []
-    for _ in range(args.steps):
-        mpts, secs, thr = ob.bench_msm(sample_log, TAU_SEED, SCALAR_SEED, cores)
-        times.append(secs)
+    for i in range(steps_total):
+        t0 = time.perf_counter()
+        lib.ko_g1_msm(bases, scal, n, out, cores)
+        dt = time.perf_counter() - t0
+        if i >= steps_total - args.steps:
+            times.append(dt)
     t = sum(times) / len(times)
-    value = (1 << sample_log) / t / 1e6
+    value = n / t / 1e6
+    same = sample_log == args.log_n
     line = {
         "impl": "reference", "metric": "bn254_g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (BN254 Fq/Fr Montgomery)", "data": "synthetic",
-        "config": {"workload": "BN254 G1 MSM 2^%d points (BASELINE config 5), CPU arm on a 2^%d sample" % (args.log_n, sample_log)},
+        "config": {"workload": "BN254 G1 MSM 2^%d points (BASELINE config 5), CPU arm on %s" % (
+                       args.log_n, "the same 2^%d points" % sample_log if same else "a 2^%d-point sample" % sample_log),
+                   "same_config": same, "cpu_sample_log_n": sample_log, "host_cores": cores,
+                   "reference_kind": "C/OpenMP port of ffjavascript's Pippenger (oracle/c); the WASM original needs Node "
+                                     "(bench/ref_node/time_msm.js)",
+                   "result_affine_hex": out.raw.hex()},
         "cpu_baseline": {"value": value, "unit": "Mpts/s", "cores": cores, "kind": "port",
                          "sample": "2^%d of the 2^%d (SRS point, scalar) pairs per step, %d threads, oracle/c Pippenger "
                                    "(ffjavascript window table)" % (sample_log, args.log_n, cores)},
@@ -196,8 +240,13 @@ def run_b200(args):
     # ---- resident inputs: this rank's SRS shard and scalar shard ----
     srs = C.c_void_p()
     curve.check(lib.kzg_srs_generate_range(ctx, as_ptr(tau.to_bytes(32, "little")), first, shard, C.byref(srs)))
+    srs_precompute_ms = None
     if not args.window:
+        torch.cuda.synchronize()
+        tp = time.perf_counter()
         curve.check(lib.kzg_srs_precompute(ctx, srs, args.table_window))   # one-off, with the SRS, before any timing
+        torch.cuda.synchronize()
+        srs_precompute_ms = (time.perf_counter() - tp) * 1e3
     scal_all = synthetic.random_fr_std(SCALAR_SEED, N)             # standard-form LE scalars, (N, 4) u64
     scal_host = torch.from_numpy(scal_all[first:first + shard].view(np.int64).copy()).pin_memory()
     del scal_all
@@ -207,7 +256,6 @@ def run_b200(args):
     sharded = ShardedSrsMsm(world, rank, dev, curve=curve, srs=srs)
     out_affine = bytearray(64)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    scal_stage = curve.alloc(shard)
 
     def barrier():
         if world > 1:
@@ -225,8 +273,7 @@ def run_b200(args):
         if world == 1:
             curve.check(lib.kzg_srs_msm_host(ctx, srs, 0, as_ptr(scal_host), shard, as_ptr(out_affine)))
         else:
-            curve.check(lib.kzg_buf_upload(ctx, scal_stage.handle, 0, as_ptr(scal_host), shard))
-            out_affine[:] = sharded.msm(scal_stage.handle, shard)
+            out_affine[:] = sharded.msm(scal_host, shard)   # kzg_srs_msm_host_partial: the upload is inside, piecewise
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -296,34 +343,46 @@ def run_b200(args):
     curve.check(lib.kzg_bench_imad_peak(ctx, 200, C.byref(imad)))
     curve.check(lib.kzg_bench_modmul_peak(ctx, 200, C.byref(modmul)))
     geom = msm_geometry(lib, ctx, srs, shard)
-    # The dominant work is the BUCKET ACCUMULATION: (from ~2^22 points per GPU) `affine_rounds` batched-affine rounds
-    # (msm_aff_forward / fq_batch_inverse / msm_aff_backward, tag 5) that halve the sorted list each time, then the
-    # XYZZ walk msm_accumulate_kernel (tag 0) over what is left.  One "launch" below = one accumulation = one MSM.
+    # The dominant work is the BUCKET ACCUMULATION: `affine_rounds` batched-affine rounds (msm_aff_forward /
+    # fq_batch_inverse / msm_aff_backward, tag 5) that halve the sorted list each time, then the XYZZ walk
+    # msm_accumulate_kernel (tag 0) over what is left.  One "launch" below = one accumulation = one MSM.
     phase_ms = (acc_ms.value + aff_ms.value) / max(1, acc_launches.value)
     walk_ms = acc_ms.value / max(1, acc_launches.value)
-    # ALGORITHMIC work: 21 760 limb-MACs per point = 16 windows x one XYZZ mixed add (10 modmul x 136).
-    # EXECUTED: shard * windows entries; an entry absorbed by an affine round costs ~6.3 modmul (3 for its share of the
-    # batch inversion incl. the 4.3 / 16 of the recursive levels, 3 for the chord formulas), one left to the walk 10.
+    # peak: wide MACs per second.  The raw IMAD.WIDE chain microbenchmark and the library's own product chain (136 counted
+    # MACs per product, 128 of them wide) are two measurements of the same pipe; the larger one is the denominator.
+    peak = max(imad.value, modmul.value * 128.0 / 136.0)
+    # ALGORITHMIC work (the progress metric): 21 760 limb-MACs per point = 16 windows x one XYZZ mixed add.
     macs_per_launch = float(shard) * 16 * MACS_PER_POINT_WINDOW
+    algorithmic = macs_per_launch / (phase_ms * 1e-3) if phase_ms > 0 else 0.0
+    # EXECUTED work: wide MACs the kernels really issue.  Counted by ncu (fmaheavy-pipe thread instructions of these
+    # kernels at this size, profiles/traffic.json, valid while the kernel sources hash the same); else modelled: an entry
+    # absorbed by an affine round ~6.3 products (3 for its share of the inversion incl. the recursive levels, 3 for the
+    # chord formulas), an entry left to the walk 10, 128 wide MACs per product.
+    counted = ncu_counted("msm_accumulation_2_%d" % args.log_n, "msm") if world == 1 else None
     entries = float(shard) * geom["windows"]
     left = entries / (1 << geom["affine_rounds"])
-    executed_macs = (left * 10 + (entries - left) * 6.3) * 136
-    achieved = macs_per_launch / (phase_ms * 1e-3) / 1e12 if phase_ms > 0 else 0.0
+    modelled_macs = (left * 10 + (entries - left) * 6.3) * 128
+    executed_macs = counted["fmaheavy_thread_instructions"] if counted else modelled_macs
+    executed = executed_macs / (phase_ms * 1e-3) if phase_ms > 0 else 0.0
     peaks, peak_kind = measured_peaks()
     affine = geom["affine_rounds"] > 0
     roofline = {
         "bound": "imad",
         "kernel": ("bucket accumulation = %d batched-affine rounds (msm_aff_forward_kernel, batch_*_kernel<FqP>, "
                    "msm_aff_backward_kernel) + msm_accumulate_kernel" % geom["affine_rounds"]) if affine else "msm_accumulate_kernel",
-        "achieved": achieved, "peak": imad.value / 1e12,
-        "unit": "Tmac/s", "frac": achieved / (imad.value / 1e12) if imad.value else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of these kernels at 2^24 points on one GPU, summed over one
-        # accumulation, from the ncu capture summarised in profiles/r01_msm_affine.md (64-byte random gathers cost 128 B)
-        "traffic": NCU_TRAFFIC_2_24 if (world == 1 and args.log_n == 24 and geom["affine_rounds"] == 4) else None,
-        "peak_source": "kzg_bench_imad_peak: IMAD.WIDE.U32 carry chains timed live on this GPU (MEASURED_PEAKS.json has no integer peak)",
-        "modmul_peak_tmacs": modmul.value / 1e12,
+        # frac = EXECUTED wide MACs / kernel time / measured pipe peak: a utilisation figure (<= 1)
+        "achieved": executed / 1e12, "peak": peak / 1e12, "unit": "Tmac/s", "frac": executed / peak if peak else None,
+        "executed_macs_source": "ncu (profiles/traffic.json)" if counted else "model (6.3 / 10 products per entry)",
+        "traffic": counted["dram_bytes"] if counted else None,
+        "algorithmic_bytes": 64.0 * entries,
+        # the SURVEY 8d unit (21 760 MACs per point whatever the kernel really does): > 1 means algorithmic savings
+        # (window table: 12-13 digits instead of 16; affine additions: ~6 products instead of 10), not a saturated pipe
+        "algorithmic_tmacs": algorithmic / 1e12, "algorithmic_frac": algorithmic / peak if peak else None,
+        "peak_source": "max(kzg_bench_imad_peak, kzg_bench_modmul_peak x 128/136): IMAD.WIDE.U32 chains timed live on this GPU "
+                       "(MEASURED_PEAKS.json has no integer peak)",
+        "imad_peak_tmacs": imad.value / 1e12, "modmul_peak_tmacs": modmul.value / 1e12,
         "algorithmic_macs_per_launch": macs_per_launch, "executed_macs_per_launch": executed_macs,
-        "executed_frac": (executed_macs / (phase_ms * 1e-3) / imad.value) if phase_ms > 0 and imad.value else None,
+        "modelled_macs_per_launch": modelled_macs,
         "kernel_ms_per_launch": phase_ms,
         "affine_rounds_ms_per_launch": aff_ms.value / max(1, acc_launches.value),
         "xyzz_walk_ms_per_launch": walk_ms,
@@ -335,12 +394,19 @@ def run_b200(args):
     # ---- the HBM-side kernels: one NTT of the size the n = 2^22 prover needs (2^24), timed live (rank 0) ----
     roofline_hbm = None
     if rank == 0 and world == 1:
-        roofline_hbm = bench_ntt(curve, 24, peaks.get("hbm_gbs"), peak_kind)
+        roofline_hbm = bench_ntt(curve, 24, peaks.get("hbm_gbs"), peak_kind, peak)
+
+    # ---- what the reference's own calls cost at every size of BASELINE config 5 (rank 0, N = 1) ----
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        sweep = bench_sweep(curve, tau, srs, scal_dev, args.log_n)
 
     # ---- grand-sum prove at n = 2^prove_log_n through the drop-in entry point (rank 0 only) ----
     prove = None
     if args.prove_log_n and rank == 0:
         prove = bench_prove(curve, args.prove_log_n, args.prove_steps, tau)
+        if args.prove_log_n2 and args.prove_log_n2 != args.prove_log_n and world == 1:
+            prove["also"] = bench_prove(curve, args.prove_log_n2, 2, tau)   # BASELINE config 4's second size
     if world > 1:
         dist.barrier()
 
@@ -376,12 +442,17 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "u32x8 (BN254 Fq/Fr Montgomery)", "data": "synthetic",
             "config": {"workload": "BN254 G1 MSM, 2^%d points total (BASELINE config 5), SRS and scalars resident" % args.log_n,
                        "points_per_gpu": shard, "parallelism": "msm-shard%d" % world,
+                       "flavour": "fixed-base window table built once per resident SRS (kzg_srs_precompute), excluded "
+                                  "from the step like the SRS load; `sweep` has the table-less numbers",
+                       "srs_precompute_ms": srs_precompute_ms,
+                       "table_bytes": 64 * shard * geom["windows"] if not args.window else 0, "host_cores": os.cpu_count(),
                        "l2": "256 MiB buffer rewritten between timed iterations; inputs (1.5 GiB) exceed L2",
                        "known_answer_ok": check},
             "e2e": {"value": N / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * shard, "d2h_bytes_per_step": 64},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "prove": prove,
+            "clocks": clocks, "roofline": roofline, "roofline_ntt": roofline_hbm, "cpu_baseline": cpu, "prove": prove,
+            "sweep": sweep,
         }
         print(json.dumps(line))
     if world > 1:
@@ -417,32 +488,96 @@ def known_answer_matches(curve, k, got_affine):
     return bytes(aff) == bytes(got_affine)
 
 
-def bench_ntt(curve, log_n, hbm_peak, peak_kind):
-    """Fr NTT of 2^log_n elements, CUDA events on the launching stream; algorithmic bytes = 64 N"""
+def bench_ntt(curve, log_n, hbm_peak, peak_kind, imad_peak):
+    """Fr NTT of 2^log_n elements, CUDA events on the launching stream.  Bound by the integer pipe, not by HBM: a 254-bit
+    butterfly is one 136-MAC product per two elements and stage, against 64 bytes per element and pass."""
     import torch
     from kzg_grandsums_study_b200 import synthetic
     n = 1 << log_n
     x = curve.to_device(synthetic.random_fr_std(77, n).tobytes())
     y = curve.alloc(n)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    best = None
-    for i in range(6):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        curve.check(curve.lib.kzg_fr_ntt(curve.ctx, x.handle, y.handle, 0))
-        b.record()
-        torch.cuda.synchronize()
-        if i >= 2:
+    best = {0: None, 1: None}
+    for inverse in (0, 1):
+        for i in range(6):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            curve.check(curve.lib.kzg_fr_ntt(curve.ctx, x.handle, y.handle, inverse))
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                t = a.elapsed_time(b)
+                best[inverse] = t if best[inverse] is None else min(best[inverse], t)
+    ms = best[0]
+    counted = ncu_counted("ntt_2_%d" % log_n, "ntt")
+    # model: per pass ~3 products per element in the butterflies (trivial twiddles skipped by whole warps), 2 at the
+    # first pass boundary (hi x lo composite twiddle), 1 at the others (mid table); N^-1 rides on the first boundary
+    passes = (log_n + 7) // 8
+    modelled = n * (3.0 * passes + 2 + max(0, passes - 2)) * 128
+    executed = counted["fmaheavy_thread_instructions"] if counted else modelled
+    rate = executed / (ms * 1e-3)
+    return {"bound": "imad", "kernel": "ntt_strided_pass_kernel x%d + ntt_last_pass_kernel (one 2^%d transform)" % (passes - 1, log_n),
+            "achieved": rate / 1e12, "peak": imad_peak / 1e12, "unit": "Tmac/s", "frac": rate / imad_peak if imad_peak else None,
+            "executed_macs_source": "ncu (profiles/traffic.json)" if counted else "model",
+            "modmul_per_element": executed / 128.0 / n, "ms": ms, "inverse_ms": best[1],
+            "traffic": counted["dram_bytes"] if counted else None, "algorithmic_bytes": 64.0 * n,
+            "hbm_gbs_algorithmic": 64.0 * n / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak, "hbm_peak_kind": peak_kind,
+            "hbm_frac_algorithmic": 64.0 * n / (ms * 1e-3) / 1e9 / hbm_peak if hbm_peak else None,
+            "note": "%d shared-memory passes (TMA bulk row loads, radix-4 register butterflies); SURVEY 8d files the NTT "
+                    "under HBM, the counters say integer pipe (fmaheavy ~80 %%)" % passes}
+
+
+def bench_sweep(curve, tau, srs_full, scal_full, log_n_max):
+    """BASELINE config 5 on one GPU, device timing (CUDA events), inputs resident:
+       raw   = kzg_g1_msm_affine on caller-supplied bases -- what G1.multiExpAffine (polynomial.js:1112) binds to: no table
+       table = kzg_srs_msm over an SRS of that size with its window table (what commit() uses)"""
+    import torch
+    from kzg_grandsums_study_b200._lib import as_ptr, KZG_BASES_ON_DEVICE, KZG_SCALARS_ON_DEVICE
+    lib, ctx = curve.lib, curve.ctx
+    out = bytearray(64)
+    bases_ptr = lib.kzg_srs_device_ptr(srs_full)
+    scal_ptr = lib.kzg_buf_device_ptr(scal_full.handle)
+
+    def timed(fn, reps=3):
+        fn()
+        best = None
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
             t = a.elapsed_time(b)
             best = t if best is None else min(best, t)
-    achieved = 64.0 * n / (best * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "ntt_strided_pass_kernel x2 + ntt_last_pass_kernel (one 2^%d transform)" % log_n,
-            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if hbm_peak else None,
-            "peak_kind": peak_kind, "ms": best,
-            # dram bytes of the three passes from profiles/r01_ntt24_full.md (one read + one write of the vector per pass)
-            "traffic": 3.07e9 if log_n == 24 else None,
-            "note": "3 shared-memory passes; each is bound by the integer pipe (fmaheavy 74-81 % in ncu), not by HBM"}
+        return best
+
+    rows = []
+    for lg in (16, 18, 20, 22, 24):
+        if lg > log_n_max:
+            break
+        n = 1 << lg
+        row = {"log_n": lg}
+        ms = timed(lambda: curve.check(lib.kzg_g1_msm_affine(ctx, bases_ptr, scal_ptr, n, KZG_BASES_ON_DEVICE | KZG_SCALARS_ON_DEVICE,
+                                                             as_ptr(out), None)))
+        row["raw_ms"] = ms
+        row["raw_mpts_s"] = n / ms / 1e3
+        raw_result = bytes(out)
+        if lg <= 22:
+            s = C.c_void_p()
+            curve.check(lib.kzg_srs_generate(ctx, as_ptr(tau.to_bytes(32, "little")), n, C.byref(s)))
+            t0 = time.perf_counter()
+            curve.check(lib.kzg_srs_precompute(ctx, s, 0))
+            torch.cuda.synchronize()
+            row["table_precompute_ms"] = (time.perf_counter() - t0) * 1e3
+            ms = timed(lambda: curve.check(lib.kzg_srs_msm(ctx, s, 0, scal_full.handle, n, as_ptr(out))))
+            row["table_ms"] = ms
+            row["table_mpts_s"] = n / ms / 1e3
+            row["same_point"] = bytes(out) == raw_result
+            lib.kzg_srs_free(ctx, s)
+        rows.append(row)
+    return {"what": "BN254 G1 MSM on 1 GPU, resident inputs, best of 3 (CUDA events): raw = kzg_g1_msm_affine on caller bases "
+                    "(no table), table = kzg_srs_msm with the SRS window table", "rows": rows}
 
 
 def bench_prove(curve, log_n, steps, tau):

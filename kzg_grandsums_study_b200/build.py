@@ -67,6 +67,20 @@ def _tree_digest():
     return h.hexdigest()
 
 
+def source_digest(names):
+    """sha256 over the named csrc files: the key under which tools/summarize_profiles.py files ncu-counted figures
+    (profiles/traffic.json) and bench.py looks them up -- a kernel edit silently invalidates nothing"""
+    h = hashlib.sha256()
+    for name in names:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+MSM_SOURCES = ["msm.cu", "field.cuh", "ec.cuh", "frops.cu"]
+NTT_SOURCES = ["ntt.cu", "field.cuh"]
+
+
 def build(verbose=False):
     """Compile every translation unit (in parallel) and link libkzgb200.so.  Returns the library path.
     A stamp next to the library (it travels to the GPU box with it) makes an unchanged tree a no-op."""

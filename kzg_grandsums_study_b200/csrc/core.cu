@@ -31,6 +31,7 @@ int ctx_set_option(kzg_ctx* ctx, const char* name, long long value) {
     else if (k == "split_max_log") t.split_max_log = reset ? def.split_max_log : (int)value;
     else if (k == "msm_merge") t.merge = reset ? def.merge : (int)value;
     else if (k == "timeline") t.timeline = reset ? 0 : (int)value;
+    else if (k == "ntt_tile") t.ntt_tile = reset ? def.ntt_tile : (int)value;
     else return set_err(ctx, KZG_ERR_ARG, "unknown option: " + k);
     return KZG_OK;
 }
@@ -281,7 +282,7 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
     // the tuning knobs, read once (kzg_ctx_set_option changes them later)
     static const char* const knobs[] = {"aff_rounds", "aff_m", "aff_chunks", "aff_min_entries_log", "aff_min_left_log",
                                         "aff_min_fill", "part_sort", "red_k0", "tail_width", "host_piece_min_log",
-                                        "split_min_log", "split_max_log", "msm_merge", "timeline"};
+                                        "split_min_log", "split_max_log", "msm_merge", "timeline", "ntt_tile"};
     for (const char* k : knobs) {
         std::string env = "KZGB200_";
         for (const char* c = k; *c; c++) env += (char)toupper(*c);
@@ -335,7 +336,9 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
     for (int d = 0; d < 2; d++) {
         cudaFree(ctx->tw_lo[d]);
         cudaFree(ctx->tw_hi[d]);
+        cudaFree(ctx->tw_mid[d]);
     }
+    for (auto* t : ctx->tw_hi_scaled) cudaFree(t);
     for (int tag = 0; tag < KZG_TIMED_TAGS; tag++)
         for (auto& pr : ctx->timed[tag]) {
             cudaEventDestroy(pr.first);

@@ -7,15 +7,17 @@
 // Structure: log2 N is split into P <= 4 passes of at most 8 bits.  With the input index written as
 // n = sum_i n_i S_i (S_i = prod_{j>i} R_j) and the output index as k = sum_i k_i prod_{j<i} R_j, pass i
 // does R_i-point DFTs over digit n_i for a tile of T consecutive columns, entirely in shared memory
-// (radix-2 DIF stages, 128-bit loads/stores, T * 32 B = 256 B contiguous per row), multiplies by the
-// inter-pass twiddle w_{N_i}^{k_i * column} and writes back in place; the last pass works on contiguous
-// rows and scatters T-wide contiguous runs into natural order.  Every element therefore crosses HBM once
-// per pass (P reads + P writes); the arithmetic (log2 N / 2 + 2P modmul per element) is what bounds it
-// on B200 -- see DESIGN.md.
+// (the tile's rows -- T * 32 B = 256 contiguous bytes each -- staged by TMA bulk copies; DIF butterflies two stages
+// at a time in registers, 128-bit shared-memory accesses), multiplies by the inter-pass twiddle
+// w_{N_i}^{k_i * column} and writes back; the last pass works on contiguous rows and scatters T-wide contiguous
+// runs into natural order.  Every element therefore crosses HBM once per pass (P reads + P writes); the arithmetic
+// (~3 products per element and pass in the butterflies, 2 at the first pass boundary, 1 at the others; N^-1 of an
+// inverse transform rides on the first boundary's table) is what bounds it on B200 -- see DESIGN.md.
 //
-// Twiddles come from two 8192-entry tables per direction, W = w_{2^26}: lo[i] = W^i, hi[j] = W^(8192 j);
-// every twiddle of a transform of size <= 2^26 is hi[.] or hi[.] * lo[.].  A zero-padded input
-// (Evaluations.fromPolynomial with extension > 1) is handled by n_in < N: the loader substitutes zeros.
+// Twiddles come from two 8192-entry tables per direction, W = w_{2^26}: lo[i] = W^i, hi[j] = W^(8192 j): every
+// twiddle of a transform of size <= 2^26 is hi[.] or hi[.] * lo[.]; plus mid[e] = w_{2^16}^e (2 MB) so that every
+// boundary below 2^16 costs one product.  A zero-padded input (Evaluations.fromPolynomial with extension > 1) is
+// handled by n_in < N: the loader substitutes zeros.
 #include <string.h>
 
 #include "common.cuh"
@@ -45,70 +47,166 @@ __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) {
 
 // In-shared-memory R-point DIF DFTs on `cols` independent columns; element (n, c) at sh[n * cols + c].
 // Output is left in bit-reversed row order.
-__device__ __forceinline__ void smem_dif(Fr* sh, uint32_t rbits, uint32_t cols, const Fr* __restrict__ tw_hi) {
+// Two radix-2 stages per shared-memory round trip: a thread holds the four elements {j, j + h/2, j + h, j + 3h/2} of a
+// block of 2h rows in registers and runs the stage of half-size h and the stage of half-size h/2 on them (a radix-4
+// butterfly; in a prime field it costs the same four products as the two radix-2 stages -- w_4 is an ordinary
+// element -- but half the loads, stores and barriers).  Butterflies are numbered column-fastest, then group, then j, so
+// that from the second round trip on j is uniform across a warp and the trivial twiddles (j = 0) are skipped by whole
+// warps instead of being executed under a mask.
+// `tw` = the R/2 twiddles w_R^i in shared memory (smem_twiddles): every stage's twiddles are powers of w_R, and a
+// warp asks for at most four distinct ones per access (broadcasts), so none of the butterflies waits for the L2.
+__device__ __forceinline__ void smem_twiddles(Fr* tw, uint32_t rbits, const Fr* __restrict__ tw_hi) {
+    const uint32_t half = (1u << rbits) >> 1;
+    const uint32_t stride = TW_SIZE >> rbits;  // w_R^i = W^(i 2^26 / R) = hi[i * 8192 / R]
+    for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) fp_store(tw + i, fp_load<FrP>(tw_hi + i * stride));
+}
+__device__ __forceinline__ void smem_dif(Fr* sh, uint32_t rbits, uint32_t cols, const Fr* tw) {
     const uint32_t R = 1u << rbits;
-    const uint32_t nbf = (R >> 1) * cols;
-    for (uint32_t h = R >> 1; h >= 1; h >>= 1) {
-        const uint32_t tw_step = TW_SIZE / (2 * h);  // w_{2h}^j = W^(j * 2^26 / 2h) = hi[j * 8192 / 2h]
-        for (uint32_t b = threadIdx.x; b < nbf; b += NTT_THREADS) {
-            uint32_t c = b % cols;
-            uint32_t jp = b / cols;
-            uint32_t j = jp & (h - 1);
-            uint32_t i0 = ((jp - j) << 1) + j;
-            uint32_t i1 = i0 + h;
-            Fr a = fp_load<FrP>(sh + i0 * cols + c);
-            Fr d = fp_load<FrP>(sh + i1 * cols + c);
-            Fr s = fp_add(a, d);
-            Fr t = fp_sub(a, d);
-            if (j != 0) t = fp_mul(t, fp_load<FrP>(tw_hi + j * tw_step));
-            fp_store(sh + i0 * cols + c, s);
-            fp_store(sh + i1 * cols + c, t);
+    uint32_t h = R >> 1;
+    while (h >= 2) {
+        const uint32_t q = h >> 1;                 // j < q
+        const uint32_t G = R / (2 * h);            // groups of 2h rows
+        const uint32_t nb = cols * G * q;          // R * cols / 4 butterflies
+        const uint32_t step = R / (2 * h);         // w_{2h}^j = w_R^(j R / 2h)
+        for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+            const uint32_t c = b % cols;
+            const uint32_t rest = b / cols;
+            const uint32_t g = rest % G;
+            const uint32_t j = rest / G;
+            Fr* p0 = sh + (g * 2 * h + j) * cols + c;
+            Fr* p1 = p0 + q * cols;
+            Fr* p2 = p0 + h * cols;
+            Fr* p3 = p2 + q * cols;
+            const Fr a0 = fp_load<FrP>(p0), a1 = fp_load<FrP>(p1), a2 = fp_load<FrP>(p2), a3 = fp_load<FrP>(p3);
+            const Fr s0 = fp_add(a0, a2), s1 = fp_add(a1, a3);
+            Fr t0 = fp_sub(a0, a2), t1 = fp_sub(a1, a3);
+            t1 = fp_mul(t1, fp_load<FrP>(tw + ((j + q) * step)));  // w_{2h}^(j + h/2)
+            if (j != 0) t0 = fp_mul(t0, fp_load<FrP>(tw + j * step));
+            Fr u1 = fp_sub(s0, s1), u3 = fp_sub(t0, t1);
+            if (j != 0) {
+                const Fr w2 = fp_load<FrP>(tw + 2 * j * step);     // w_h^j
+                u1 = fp_mul(u1, w2);
+                u3 = fp_mul(u3, w2);
+            }
+            fp_store(p0, fp_add(s0, s1));
+            fp_store(p1, u1);
+            fp_store(p2, fp_add(t0, t1));
+            fp_store(p3, u3);
+        }
+        __syncthreads();
+        h >>= 2;
+    }
+    if (h == 1) {  // odd number of stages: one twiddle-free radix-2 stage is left
+        const uint32_t nb = cols * (R >> 1);
+        for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+            const uint32_t c = b % cols, g = b / cols;
+            Fr* p0 = sh + (2 * g) * cols + c;
+            Fr* p1 = p0 + cols;
+            const Fr a = fp_load<FrP>(p0), d = fp_load<FrP>(p1);
+            fp_store(p0, fp_add(a, d));
+            fp_store(p1, fp_sub(a, d));
         }
         __syncthreads();
     }
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP): a tile row is 256 contiguous bytes of global memory ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // strided (non-last) pass.  grid = N / (R * T).
-__global__ void __launch_bounds__(NTT_THREADS) ntt_strided_pass_kernel(const Fr* __restrict__ src, uint64_t n_in,
-                                                                       Fr* __restrict__ dst, uint32_t rbits,
-                                                                       uint32_t log_stride, uint32_t log_n,
+// The tile -- R rows of T * 32 = 256 contiguous bytes, S elements apart -- is staged in shared memory by the TMA unit:
+// thread n issues ONE bulk copy for row n and the block waits on an mbarrier for the R * 256 bytes; rows beyond the
+// valid input (zero-padded transforms, Evaluations.fromPolynomial with an extension) are zero-filled by the threads.
+// Inter-pass twiddle w_{N_i}^(k * column), N_i = R * S: one product with the 2^16-entry `mid` table when N_i <= 2^16,
+// the hi x lo composite otherwise; `scaled` (inverse transforms, first pass): the hi table carries the factor N^-1.
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_strided_pass_kernel(const Fr* __restrict__ src, uint64_t n_in,
+                                                                       Fr* __restrict__ dst, uint32_t rbits, uint32_t T,
+                                                                       uint32_t log_stride, uint32_t use_mid, uint32_t scaled,
                                                                        const Fr* __restrict__ tw_lo,
-                                                                       const Fr* __restrict__ tw_hi) {
+                                                                       const Fr* __restrict__ tw_hi_butterfly,
+                                                                       const Fr* __restrict__ tw_hi_boundary,
+                                                                       const Fr* __restrict__ tw_mid) {
     extern __shared__ uint4 smem_raw[];
     Fr* sh = reinterpret_cast<Fr*>(smem_raw);
+    __shared__ __align__(8) uint64_t bar;
     const uint32_t R = 1u << rbits;
-    const uint32_t T = NTT_TILE_COLS;
     const uint64_t S = 1ull << log_stride;
     const uint64_t tiles_per_group = S / T;  // column tiles inside one (hi) group
     const uint64_t grp = blockIdx.x / tiles_per_group;
     const uint64_t c0 = (blockIdx.x % tiles_per_group) * T;
     const uint64_t base = grp * (S << rbits) + c0;
-    for (uint32_t idx = threadIdx.x; idx < R * T; idx += NTT_THREADS) {
-        uint32_t c = idx % T, n = idx / T;
-        uint64_t gi = base + (uint64_t)n * S + c;
-        Fr v = gi < n_in ? fp_load<FrP>(src + gi) : fp_zero<FrP>();
-        fp_store(sh + idx, v);
+    // rows whose T elements are all valid come through the TMA unit
+    uint32_t full_rows = 0;
+    if (n_in >= base + T) {
+        const uint64_t r = (n_in - base - T) / S + 1;
+        full_rows = r < R ? (uint32_t)r : R;
+    }
+    Fr* tw = sh + R * T;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, full_rows * T * (uint32_t)sizeof(Fr));
     }
     __syncthreads();
-    smem_dif(sh, rbits, T, tw_hi);
+    for (uint32_t n = threadIdx.x; n < R; n += blockDim.x) {
+        if (n < full_rows) {
+            bulk_load(sh + n * T, src + base + (uint64_t)n * S, T * (uint32_t)sizeof(Fr), &bar);
+        } else {
+            for (uint32_t c = 0; c < T; c++) {
+                const uint64_t gi = base + (uint64_t)n * S + c;
+                fp_store(sh + n * T + c, gi < n_in ? fp_load<FrP>(src + gi) : fp_zero<FrP>());
+            }
+        }
+    }
+    smem_twiddles(tw, rbits, tw_hi_butterfly);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    smem_dif(sh, rbits, T, tw);
     // twiddle w_{N_i}^{k * col}, N_i = R * S : exponent in units of W = w_{2^26}
     const uint32_t log_ni = rbits + log_stride;
     const uint32_t shift = NTT_MAX_LOG - log_ni;
-    (void)log_n;
-    for (uint32_t idx = threadIdx.x; idx < R * T; idx += NTT_THREADS) {
+    for (uint32_t idx = threadIdx.x; idx < R * T; idx += blockDim.x) {
         uint32_t c = idx % T, p = idx / T;
         uint32_t k = bitrev(p, rbits);
         Fr v = fp_load<FrP>(sh + idx);
         uint64_t col = c0 + c;
         uint64_t e = ((uint64_t)k * col) & ((1ull << log_ni) - 1);
-        if (e != 0) v = fp_mul(v, tw_lookup(tw_lo, tw_hi, (uint32_t)(e << shift)));
+        if (use_mid) {
+            if (e != 0) v = fp_mul(v, fp_load<FrP>(tw_mid + (e << (16 - log_ni))));
+        } else if (scaled || e != 0) {
+            v = fp_mul(v, tw_lookup(tw_lo, tw_hi_boundary, (uint32_t)(e << shift)));
+        }
         fp_store(dst + base + (uint64_t)k * S + c, v);
     }
 }
 
 // last pass: rows of R contiguous elements; a tile is T rows that are consecutive in k_1.
 // grid = N / (R * T)   (T = 1 when npass == 1)
-__global__ void __launch_bounds__(NTT_THREADS) ntt_last_pass_kernel(const Fr* __restrict__ src, uint64_t n_in,
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_last_pass_kernel(const Fr* __restrict__ src, uint64_t n_in,
                                                                     Fr* __restrict__ dst, NttPlan plan, uint32_t T,
                                                                     const Fr* __restrict__ tw_hi, Fr scale,
                                                                     bool do_scale) {
@@ -124,35 +222,34 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_last_pass_kernel(const Fr* __
     const uint64_t mid = blockIdx.x % M;
     const uint64_t k1_0 = (blockIdx.x / M) * T;
     const uint32_t log_s1 = plan.log_n - plan.radbits[0];  // S_1 = N / R_1   (only used when P > 1)
-    for (uint32_t idx = threadIdx.x; idx < R * T; idx += NTT_THREADS) {
+    for (uint32_t idx = threadIdx.x; idx < R * T; idx += blockDim.x) {
         uint32_t n = idx % R, r = idx / R;
         uint64_t gi = (P > 1 ? ((k1_0 + r) << log_s1) : 0) + (mid << rbits) + n;
         Fr v = gi < n_in ? fp_load<FrP>(src + gi) : fp_zero<FrP>();
         fp_store(sh + n * T + r, v);
     }
+    Fr* tw = sh + R * T;
+    smem_twiddles(tw, rbits, tw_hi);
     __syncthreads();
-    smem_dif(sh, rbits, T, tw_hi);
+    smem_dif(sh, rbits, T, tw);
     // output index = k_1 + R_1 * (digit-reversed mid) + k_P * (N / R_P)
     uint64_t out_mid = 0;
     if (P > 2) {
         // storage order of mid: k_2 most significant ... k_{P-1} least; output order: k_2 least significant
         uint64_t rest = mid;
-        uint32_t mult_bits = mid_bits;
         for (uint32_t j = P - 2; j >= 1; j--) {
             uint32_t kb = plan.radbits[j];
             uint64_t kj = rest & ((1ull << kb) - 1);
             rest >>= kb;
-            mult_bits -= kb;
             // digit j has output weight prod_{1<m<j} R_m  (relative to R_1)
             uint32_t wbits = 0;
             for (uint32_t m = 1; m < j; m++) wbits += plan.radbits[m];
             out_mid += kj << wbits;
             if (j == 1) break;
         }
-        (void)mult_bits;
     }
     const uint32_t log_hi = plan.log_n - rbits;  // N / R_P
-    for (uint32_t idx = threadIdx.x; idx < R * T; idx += NTT_THREADS) {
+    for (uint32_t idx = threadIdx.x; idx < R * T; idx += blockDim.x) {
         uint32_t r = idx % T, p = idx / T;
         uint32_t k = bitrev(p, rbits);
         Fr v = fp_load<FrP>(sh + p * T + r);
@@ -208,16 +305,48 @@ Fr fr_root_of_unity(uint32_t log_n) {
     return w;
 }
 
+// mid[e] = W^(e 2^10) = w_{2^16}^e: the inter-pass twiddles of every boundary with N_i <= 2^16 in ONE product
+__global__ void tw_mid_kernel(Fr* __restrict__ mid, const Fr* __restrict__ lo, const Fr* __restrict__ hi) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (1u << 16)) return;
+    const uint32_t x = e << 10;
+    Fr v = fp_load<FrP>(hi + (x >> TW_BITS));
+    const uint32_t l = x & (TW_SIZE - 1);
+    if (l) v = fp_mul(v, fp_load<FrP>(lo + l));
+    fp_store(mid + e, v);
+}
+__global__ void tw_scale_kernel(Fr* __restrict__ out, const Fr* __restrict__ in, Fr scale) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < TW_SIZE) fp_store(out + i, fp_mul(fp_load<FrP>(in + i), scale));
+}
+
 int ntt_init_tables(kzg_ctx* ctx) {
     for (int dir = 0; dir < 2; dir++) {
         KZG_CUDA(ctx, cudaMalloc((void**)&ctx->tw_lo[dir], sizeof(Fr) * TW_SIZE));
         KZG_CUDA(ctx, cudaMalloc((void**)&ctx->tw_hi[dir], sizeof(Fr) * TW_SIZE));
+        KZG_CUDA(ctx, cudaMalloc((void**)&ctx->tw_mid[dir], sizeof(Fr) << 16));
         Fr w = fr_root_of_unity(NTT_MAX_LOG);
         if (dir == 1) w = fp_inv(w);
         Fr w_hi = fp_pow_u64(w, TW_SIZE);
         KZG_LAUNCH(ctx, tw_table_kernel, TW_SIZE / 256, 256, 0, ctx->tw_lo[dir], ctx->tw_hi[dir], w, w_hi);
+        KZG_LAUNCH(ctx, tw_mid_kernel, (1u << 16) / 256, 256, 0, ctx->tw_mid[dir], ctx->tw_lo[dir], ctx->tw_hi[dir]);
     }
     KZG_CHECK_LAUNCH(ctx);
+    return KZG_OK;
+}
+
+// inverse transforms of 2^log_n points: the hi table of the inverse direction times N^-1 (built on first use, 256 KB)
+static int ntt_scaled_hi(kzg_ctx* ctx, uint32_t log_n, const Fr** out) {
+    if (!ctx->tw_hi_scaled[log_n]) {
+        Fr* t = nullptr;
+        KZG_CUDA(ctx, cudaMalloc((void**)&t, sizeof(Fr) * TW_SIZE));
+        const Fr scale = fp_inv(fr_from_u64_host(1ull << log_n));
+        KZG_LAUNCH(ctx, tw_scale_kernel, TW_SIZE / 256, 256, 0, t, ctx->tw_hi[1], scale);
+        KZG_CHECK_LAUNCH(ctx);
+        KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // one-off: the other lane's stream may use the table next
+        ctx->tw_hi_scaled[log_n] = t;
+    }
+    *out = ctx->tw_hi_scaled[log_n];
     return KZG_OK;
 }
 
@@ -247,33 +376,49 @@ int ntt_run(kzg_ctx* ctx, const Fr* in, uint64_t n_in, Fr* out, uint32_t log_n, 
     }
     if (plan.npass == 1) {
         const uint32_t R = 1u << log_n;
-        KZG_LAUNCH(ctx, ntt_last_pass_kernel, 1, NTT_THREADS, sizeof(Fr) * R, in, n_in, out, plan, 1u, ctx->tw_hi[dir],
+        KZG_LAUNCH(ctx, ntt_last_pass_kernel, 1, NTT_THREADS, sizeof(Fr) * (R + R / 2), in, n_in, out, plan, 1u, ctx->tw_hi[dir],
                    scale, inverse);
         KZG_CHECK_LAUNCH(ctx);
         return KZG_OK;
     }
+    const Fr* hi_scaled = nullptr;
+    if (inverse) KZG_TRY(ntt_scaled_hi(ctx, log_n, &hi_scaled));  // (the first pass applies N^-1 with its twiddles)
     Fr* tmp = nullptr;
     KZG_CUDA(ctx, cudaMallocAsync((void**)&tmp, sizeof(Fr) * N, ctx->stream));
+    // tile width T (columns = contiguous elements per row) and threads per block: one thread per two radix-4 butterflies
+    const uint32_t T = ctx->tuning.ntt_tile == 4 ? 4u : NTT_TILE_COLS;
     uint32_t log_stride = log_n;
     const Fr* src = in;
     uint64_t src_n = n_in;
+    timed_begin(ctx, KZG_TIMED_NTT);
     for (uint32_t i = 0; i + 1 < plan.npass; i++) {
         const uint32_t rb = plan.radbits[i];
+        const uint32_t log_ni = log_stride;  // N_i = R_i * S_i = the stride before this pass
         log_stride -= rb;
         const uint32_t R = 1u << rb;
-        const uint32_t grid = (uint32_t)(N / ((uint64_t)R * NTT_TILE_COLS));
-        KZG_LAUNCH(ctx, ntt_strided_pass_kernel, grid, NTT_THREADS, sizeof(Fr) * R * NTT_TILE_COLS, src, src_n, tmp, rb,
-                   log_stride, log_n, ctx->tw_lo[dir], ctx->tw_hi[dir]);
+        const uint32_t grid = (uint32_t)(N / ((uint64_t)R * T));
+        const uint32_t scaled = inverse && i == 0 ? 1u : 0u;
+        const uint32_t use_mid = !scaled && log_ni <= 16 ? 1u : 0u;
+        uint32_t threads = R * T / 8;
+        if (threads > NTT_THREADS) threads = NTT_THREADS;
+        if (threads < 32) threads = 32;
+        KZG_LAUNCH(ctx, ntt_strided_pass_kernel, grid, threads, sizeof(Fr) * (R * T + R / 2), src, src_n, tmp, rb, T,
+                   log_stride, use_mid, scaled, ctx->tw_lo[dir], ctx->tw_hi[dir], scaled ? hi_scaled : ctx->tw_hi[dir],
+                   ctx->tw_mid[dir]);
         src = tmp;
         src_n = N;
     }
     {
         const uint32_t rb = plan.radbits[plan.npass - 1];
         const uint32_t R = 1u << rb;
-        const uint32_t grid = (uint32_t)(N / ((uint64_t)R * NTT_TILE_COLS));
-        KZG_LAUNCH(ctx, ntt_last_pass_kernel, grid, NTT_THREADS, sizeof(Fr) * R * NTT_TILE_COLS, tmp, N, out, plan,
-                   NTT_TILE_COLS, ctx->tw_hi[dir], scale, inverse);
+        const uint32_t grid = (uint32_t)(N / ((uint64_t)R * T));
+        uint32_t threads = R * T / 8;
+        if (threads > NTT_THREADS) threads = NTT_THREADS;
+        if (threads < 32) threads = 32;
+        KZG_LAUNCH(ctx, ntt_last_pass_kernel, grid, threads, sizeof(Fr) * (R * T + R / 2), tmp, N, out, plan, T, ctx->tw_hi[dir],
+                   scale, false);
     }
+    timed_end(ctx, KZG_TIMED_NTT);
     KZG_CHECK_LAUNCH(ctx);
     KZG_CUDA(ctx, cudaFreeAsync(tmp, ctx->stream));
     return KZG_OK;

@@ -480,3 +480,22 @@ def test_msm_huge_buckets(curve, tau, part_sort, monkeypatch):
     finally:
         curve.set_option("part_sort", -1)
         curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+@pytest.mark.parametrize("tile", [4, 8])
+def test_ntt_tile_widths(curve, tile):
+    """both tile widths of the pass kernels (256-byte rows / 128-byte rows) against the oracle, sizes with an odd and
+    an even number of stages per pass, forward, inverse and zero-padded"""
+    try:
+        curve.set_option("ntt_tile", tile)
+        for log_n in (11, 12, 13, 14):
+            n = 1 << log_n
+            a = col(900 + log_n, n)
+            assert from_mont(curve.Fr.fft(mont_bytes(a)).tobytes()) == opoly.ntt(a)
+            assert from_mont(curve.Fr.ifft(mont_bytes(a)).tobytes()) == opoly.ntt(a, inverse=True)
+        from kzg_grandsums_study_b200.polynomial import Evaluations, Polynomial
+        coefs = col(951, 3000)
+        ev = Evaluations.fromPolynomial(Polynomial(mont_bytes(coefs), curve), 4, curve)
+        assert from_mont(ev.eval.tobytes()) == opoly.ntt(coefs + [0] * (16384 - 3000))
+    finally:
+        curve.set_option("ntt_tile", -1)

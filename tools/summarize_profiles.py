@@ -5,6 +5,11 @@
   python tools/summarize_profiles.py multi <csv> <out.md> <title> <first kernel of the sequence to keep>
       (csv of `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
        sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed --csv`: one row per launch and metric)
+  python tools/summarize_profiles.py traffic <csv> <key> <first kernel> <kernel-name regex> <msm|ntt> [note]
+      (same csv plus sm__inst_executed_pipe_fmaheavy.sum and smsp__thread_inst_executed_per_inst_executed.ratio): sums DRAM
+      bytes and fmaheavy thread-instructions (= executed wide MACs) over the matching launches of the LAST sequence that
+      starts with <first kernel> and files them in profiles/traffic.json under <key> together with the hash of the
+      kernel sources -- bench.py reports them only while that hash still matches.
 """
 import collections
 import csv
@@ -74,6 +79,35 @@ def multi(path, out, title, first_kernel):
         f.write("```\n")
 
 
+def traffic(path, key, first_kernel, pattern, family, note=""):
+    import json
+    import os
+    import re
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from kzg_grandsums_study_b200 import build as b
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    ix = {h: i for i, h in enumerate(rows[0])}
+    data = collections.OrderedDict()
+    for r in rows[1:]:
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("kzg::", "").strip()
+        data.setdefault((int(r[ix["ID"]]), name), {})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
+    items = list(data.items())
+    starts = [i for i, ((_, k), _m) in enumerate(items) if k.startswith(first_kernel)]
+    seq = items[starts[-1]:]
+    rx = re.compile(pattern)
+    sel = [(k, m) for (_, k), m in seq if rx.search(k)]
+    dram = sum(m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"] for _, m in sel)
+    macs = sum(m["sm__inst_executed_pipe_fmaheavy.sum"] * m["smsp__thread_inst_executed_per_inst_executed.ratio"] for _, m in sel)
+    ms = sum(m["gpu__time_duration.sum"] for _, m in sel) / 1e6
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    table = json.load(open(out)) if os.path.exists(out) else {}
+    table[key] = {"src_sha16": b.source_digest(b.MSM_SOURCES if family == "msm" else b.NTT_SOURCES),
+                  "dram_bytes": dram, "fmaheavy_thread_instructions": macs, "kernel_ms_under_ncu": ms, "launches": len(sel),
+                  "kernels": sorted(set(k for k, _ in sel)), "source_csv": os.path.basename(path), "note": note}
+    json.dump(table, open(out, "w"), indent=1, sort_keys=True)
+    print(key, json.dumps(table[key]))
+
+
 WANT = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
     "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -111,6 +145,9 @@ def full(path, out, title):
             f.write("\n")
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "traffic":
+    traffic(*sys.argv[2:])
+    sys.exit(0)
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "multi":
     multi(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
     sys.exit(0)
