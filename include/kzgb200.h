@@ -80,6 +80,9 @@ int kzg_ctx_kernel_time(kzg_ctx* ctx, uint32_t which, int reset, double* ms_out,
  * validates magic "ptau", version <= 1, exactly one header section, n8 == 32, q == BN254 q, header size;
  * uploads the first n_points of section 2 (clamped to the section).  power_out may be NULL. */
 int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs** out, uint32_t* power_out);
+/* the same for the points [first, first + n_points) only: one device's shard of a multi-GPU SRS */
+int kzg_srs_load_ptau_range(kzg_ctx* ctx, const char* path, uint64_t first, uint64_t n_points, kzg_srs** out,
+                            uint32_t* power_out);
 /* header only (ptau_utils.js:3-24): power, ceremonyPower */
 int kzg_ptau_read_header(kzg_ctx* ctx, const char* path, uint32_t* power, uint32_t* ceremony_power);
 /* [tau]_2 : second G2 point of section 3, 128 bytes (verifier.js:18-19) */
@@ -180,6 +183,31 @@ int kzg_msm_geometry(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uin
 int kzg_msm_plan(kzg_ctx* ctx, kzg_srs* srs, uint64_t n, int montgomery, uint32_t* window_bits, uint32_t* windows,
                  uint32_t* affine_rounds);
 int kzg_msm_set_window(kzg_ctx* ctx, uint32_t c);
+
+/* ---- multi-GPU MSM inside one process (a Node addon cannot run one process per GPU) ----------------------- */
+/* G1.multiExpAffine / commit over an SRS sharded across devices (polynomial.js:1106-1115).  Device g keeps the contiguous
+ * slice [first_g, first_g + count_g) of the SRS resident with its window table, reduces the matching scalars to ONE
+ * 128-byte partial point, device 0 pulls the partials with peer copies and normalises.  devices = NULL / n = 0: all
+ * visible devices.  One context per device (kzg_mgpu_ctx), one host thread per device during a call. */
+typedef struct kzg_mgpu kzg_mgpu;
+int kzg_mgpu_create(const int* devices, uint32_t n_devices, kzg_mgpu** out);
+int kzg_mgpu_destroy(kzg_mgpu* m);
+uint32_t kzg_mgpu_device_count(kzg_mgpu* m);
+kzg_ctx* kzg_mgpu_ctx(kzg_mgpu* m, uint32_t i);
+const char* kzg_mgpu_last_error(kzg_mgpu* m);
+uint64_t kzg_mgpu_srs_len(kzg_mgpu* m);
+int kzg_mgpu_shard(kzg_mgpu* m, uint32_t i, uint64_t* first, uint64_t* count);
+int kzg_mgpu_srs_generate(kzg_mgpu* m, const uint8_t tau_std[32], uint64_t n_points);
+int kzg_mgpu_srs_from_host(kzg_mgpu* m, const uint8_t* affine, uint64_t n_points);
+int kzg_mgpu_srs_load_ptau(kzg_mgpu* m, const char* path, uint64_t n_points);   /* prover.js:15-16,83-85 */
+/* scalars in HOST memory (n x 32 B standard form, n <= |SRS|); uploads piecewise under the pieces' MSMs */
+int kzg_mgpu_srs_msm_host(kzg_mgpu* m, const void* scalars_std_host, uint64_t n, uint8_t out_affine[64]);
+/* scalars made resident once, then any number of MSMs over them */
+int kzg_mgpu_scalars_upload(kzg_mgpu* m, const void* scalars_std_host, uint64_t n);
+int kzg_mgpu_srs_msm(kzg_mgpu* m, uint8_t out_affine[64]);
+/* page-lock / release a caller-owned host buffer for all devices (so that uploads overlap compute) */
+int kzg_host_register(void* ptr, uint64_t bytes);
+int kzg_host_unregister(void* ptr);
 
 /* ---- fused provers (prover.js:144-413 and the grand-product twin) --------------------------------------- */
 /* The Keccak transcript stays with the caller: each round returns the bytes the transcript needs and the

@@ -31,6 +31,7 @@ SIGNATURES = {
     "kzg_bench_modmul_peak": (i32, [vp, u32, C.POINTER(C.c_double)]),
     "kzg_ctx_kernel_time": (i32, [vp, u32, i32, C.POINTER(C.c_double), C.POINTER(u64)]),
     "kzg_srs_load_ptau": (i32, [vp, C.c_char_p, u64, C.POINTER(vp), C.POINTER(u32)]),
+    "kzg_srs_load_ptau_range": (i32, [vp, C.c_char_p, u64, u64, C.POINTER(vp), C.POINTER(u32)]),
     "kzg_ptau_read_header": (i32, [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32)]),
     "kzg_ptau_read_tau_g2": (i32, [vp, C.c_char_p, vp]),
     "kzg_srs_from_host": (i32, [vp, vp, u64, C.POINTER(vp)]),
@@ -81,6 +82,21 @@ SIGNATURES = {
     "kzg_msm_geometry": (i32, [vp, vp, u64, i32, C.POINTER(u32), C.POINTER(u32)]),
     "kzg_msm_plan": (i32, [vp, vp, u64, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
     "kzg_msm_set_window": (i32, [vp, u32]),
+    "kzg_mgpu_create": (i32, [C.POINTER(i32), u32, C.POINTER(vp)]),
+    "kzg_mgpu_destroy": (i32, [vp]),
+    "kzg_mgpu_device_count": (u32, [vp]),
+    "kzg_mgpu_ctx": (vp, [vp, u32]),
+    "kzg_mgpu_last_error": (C.c_char_p, [vp]),
+    "kzg_mgpu_srs_len": (u64, [vp]),
+    "kzg_mgpu_shard": (i32, [vp, u32, C.POINTER(u64), C.POINTER(u64)]),
+    "kzg_mgpu_srs_generate": (i32, [vp, vp, u64]),
+    "kzg_mgpu_srs_from_host": (i32, [vp, vp, u64]),
+    "kzg_mgpu_srs_load_ptau": (i32, [vp, C.c_char_p, u64]),
+    "kzg_mgpu_srs_msm_host": (i32, [vp, vp, u64, vp]),
+    "kzg_mgpu_scalars_upload": (i32, [vp, vp, u64]),
+    "kzg_mgpu_srs_msm": (i32, [vp, vp]),
+    "kzg_host_register": (i32, [vp, u64]),
+    "kzg_host_unregister": (i32, [vp]),
     "kzg_prover_create": (i32, [vp, vp, i32, u32, u32, i32, C.POINTER(vp)]),
     "kzg_prover_destroy": (i32, [vp]),
     "kzg_prover_round1": (i32, [vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp]),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libkzgb200.so")
-SOURCES = ["core.cu", "host.cu", "frops.cu", "ntt.cu", "argument.cu", "msm.cu", "srs.cu", "prover.cu"]
+SOURCES = ["core.cu", "host.cu", "frops.cu", "ntt.cu", "argument.cu", "msm.cu", "srs.cu", "prover.cu", "mgpu.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

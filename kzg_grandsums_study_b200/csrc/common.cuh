@@ -17,7 +17,7 @@ struct MsmTuning {
     uint32_t aff_m = 16;            // output points per thread of a round
     int aff_chunks = 0;             // chunks a round is launched in (inversion hidden under the other chunks); 0: auto
     uint64_t aff_min_entries = 20ull << 20;  // no rounds below this many bucket entries
-    uint64_t aff_min_left = 1ull << 22;      // a round must leave at least this many points
+    uint64_t aff_min_left = 13ull << 19;     // a round must leave at least this many points (6.8 M: measured, r02_msm_rounds.md)
     double aff_min_fill = 6.0;      // ... and find at least this many entries per bucket
     int part_sort = -1;             // 0 / 1: direct counting sort / two-level partition sort; -1: by size
     int red_k0 = -1;                // log2 of the level-0 radix of the bucket reduction; -1: by size

@@ -166,7 +166,9 @@ int kzg_srs_from_host(kzg_ctx* ctx, const uint8_t* affine, uint64_t n_points, kz
     return KZG_OK;
 }
 
-int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs** out, uint32_t* power_out) {
+// the points [first, first + n_points) of section 2 (clamped to the section): the shard of one device
+int kzg_srs_load_ptau_range(kzg_ctx* ctx, const char* path, uint64_t first, uint64_t n_points, kzg_srs** out,
+                            uint32_t* power_out) {
     kzg::DeviceGuard _dg(ctx);
     if (!ctx || !path || !out) return KZG_ERR_ARG;
     FILE* f = fopen(path, "rb");
@@ -181,10 +183,11 @@ int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs
         return r;
     }
     const PtauSection s2 = sections[2][0];
-    uint64_t avail = s2.size / 64;
-    uint64_t n = n_points < avail ? n_points : avail;  // the reference over-reads by one point at n = 2^power
+    const uint64_t avail = s2.size / 64;
+    const uint64_t lo = first < avail ? first : avail;
+    const uint64_t n = n_points < avail - lo ? n_points : avail - lo;  // the reference over-reads by one point at n = 2^power
     std::vector<uint8_t> host((size_t)n * 64);
-    if (n && (fseeko(f, (off_t)s2.offset, SEEK_SET) != 0 || fread(host.data(), 1, host.size(), f) != host.size())) {
+    if (n && (fseeko(f, (off_t)(s2.offset + 64 * lo), SEEK_SET) != 0 || fread(host.data(), 1, host.size(), f) != host.size())) {
         fclose(f);
         return set_err(ctx, KZG_ERR_IO, std::string(path) + ": short read in tauG1");
     }
@@ -195,6 +198,10 @@ int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs
     if (power_out) *power_out = power;
     *out = s;
     return KZG_OK;
+}
+
+int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs** out, uint32_t* power_out) {
+    return kzg_srs_load_ptau_range(ctx, path, 0, n_points, out, power_out);
 }
 
 int kzg_srs_generate(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t n_points, kzg_srs** out) {

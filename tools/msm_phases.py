@@ -1,5 +1,6 @@
 """Per-phase device times of the SRS (window-table) MSM, CUDA events on the launching stream:
-python tools/msm_phases.py [LOG_N ...]   ->  sort (digits/scan/scatter) | accumulate | reduce | finish | whole call"""
+python tools/msm_phases.py [LOG_N ...]   ->  sort (digits/scan/scatter) | accumulate | reduce | finish | whole call
+ROUNDS="0,1,2" CHUNKS="1,2" sweep the number of batched-affine rounds / chunks per round for every size (-1 = library default)"""
 import ctypes as C
 import os
 import sys
@@ -28,22 +29,27 @@ for log_n in sizes:
     out = bytearray(64)
     wb, nw = C.c_uint32(), C.c_uint32()
     curve.check(lib.kzg_msm_geometry(ctx, srs, n, 0, C.byref(wb), C.byref(nw)))
-    for _ in range(3):
-        curve.check(lib.kzg_srs_msm(ctx, srs, 0, scal.handle, n, as_ptr(out)))
-    reps = 5
-    curve.check(lib.kzg_ctx_kernel_time(ctx, 0, 1, None, None))
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        curve.check(lib.kzg_srs_msm(ctx, srs, 0, scal.handle, n, as_ptr(out)))
-    torch.cuda.synchronize()
-    wall = (time.perf_counter() - t0) * 1e3 / reps
-    parts = []
-    for name, tag in TAGS:
-        ms, cnt = C.c_double(), C.c_uint64()
-        curve.check(lib.kzg_ctx_kernel_time(ctx, tag, 0, C.byref(ms), C.byref(cnt)))
-        parts.append("%s %.3f" % (name, ms.value / reps))
-    curve.check(lib.kzg_ctx_kernel_time(ctx, 0, -1, None, None))
-    print("msm 2^%d c=%d windows=%d: %s | call %.3f ms" % (log_n, wb.value, nw.value, " | ".join(parts), wall), flush=True)
+    for rounds in [int(x) for x in os.environ.get("ROUNDS", "-1").split(",")]:
+        for chunks in [int(x) for x in os.environ.get("CHUNKS", "-1").split(",")]:
+            curve.set_option("aff_rounds", rounds)
+            curve.set_option("aff_chunks", chunks)
+            for _ in range(3):
+                curve.check(lib.kzg_srs_msm(ctx, srs, 0, scal.handle, n, as_ptr(out)))
+            reps = 5
+            curve.check(lib.kzg_ctx_kernel_time(ctx, 0, 1, None, None))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                curve.check(lib.kzg_srs_msm(ctx, srs, 0, scal.handle, n, as_ptr(out)))
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3 / reps
+            parts = []
+            for name, tag in TAGS:
+                ms, cnt = C.c_double(), C.c_uint64()
+                curve.check(lib.kzg_ctx_kernel_time(ctx, tag, 0, C.byref(ms), C.byref(cnt)))
+                parts.append("%s %.3f" % (name, ms.value / reps))
+            curve.check(lib.kzg_ctx_kernel_time(ctx, 0, -1, None, None))
+            print("msm 2^%d c=%d windows=%d rounds=%d chunks=%d: %s | call %.3f ms" % (
+                log_n, wb.value, nw.value, rounds, chunks, " | ".join(parts), wall), flush=True)
     del scal
     lib.kzg_srs_free(ctx, srs)
