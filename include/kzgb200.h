@@ -93,6 +93,11 @@ int kzg_srs_from_host(kzg_ctx* ctx, const uint8_t* affine, uint64_t n_points, kz
 int kzg_srs_generate(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t n_points, kzg_srs** out);
 /* the slice [tau^i]_1, first <= i < first + n_points: the shard of one GPU in the multi-GPU MSM */
 int kzg_srs_generate_range(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t first, uint64_t n_points, kzg_srs** out);
+/* Lagrange-basis SRS: [L_i(tau)]_1 for i < 2^n_bits, the inverse DFT of the first 2^n_bits monomial points
+ * carried out in the group (one-off, ~0.6 s at 2^20).  kzg_commit / kzg_commit_many over it take a polynomial's EVALUATIONS
+ * on H (Montgomery) and return the same point as committing iNTT(evaluations) over the monomial SRS -- the commitments of
+ * F, T, S / Z (prover.js:151-162; grandsum.js:61) without their iNTTs. */
+int kzg_srs_lagrange(kzg_ctx* ctx, kzg_srs* srs, uint32_t n_bits, kzg_srs** out);
 /* write a .ptau (sections 1,2,3) from a device SRS; tau_g2 = 128 B [tau]_2 (host computed by the caller) */
 int kzg_srs_write_ptau(kzg_ctx* ctx, kzg_srs* srs, uint32_t power, const uint8_t g2_one[128],
                        const uint8_t g2_tau[128], const char* path);

@@ -37,6 +37,7 @@ SIGNATURES = {
     "kzg_srs_from_host": (i32, [vp, vp, u64, C.POINTER(vp)]),
     "kzg_srs_generate": (i32, [vp, vp, u64, C.POINTER(vp)]),
     "kzg_srs_generate_range": (i32, [vp, vp, u64, u64, C.POINTER(vp)]),
+    "kzg_srs_lagrange": (i32, [vp, vp, u32, C.POINTER(vp)]),
     "kzg_srs_write_ptau": (i32, [vp, vp, u32, vp, vp, C.c_char_p]),
     "kzg_srs_download": (i32, [vp, vp, u64, u64, vp]),
     "kzg_srs_len": (u64, [vp]),

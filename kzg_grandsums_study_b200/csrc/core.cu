@@ -241,6 +241,13 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
     if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return KZG_ERR_CUDA;  // no CPU fallback
     kzg_ctx* ctx = new kzg_ctx();
     ctx->device = device;
+    struct Restore {  // the caller's current device is left as it was (several contexts per process)
+        int prev = -1;
+        Restore() { cudaGetDevice(&prev); }
+        ~Restore() {
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+    } restore;
     if (cudaSetDevice(device) != cudaSuccess) {
         delete ctx;
         return KZG_ERR_CUDA;

@@ -107,6 +107,93 @@ __global__ void __launch_bounds__(128) srs_points_kernel(const G1XYZZ* __restric
     fp_store(&out[i].y, a.y);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lagrange-basis SRS:  [L_i(tau)]_1 = (1/n) sum_j w^(-ij) [tau^j]_1  -- the inverse DFT of the
+// monomial points, carried out in the GROUP: radix-2 DIF stages over extended-Jacobian points, one thread per
+// butterfly, the twiddle applied as a 254-bit double-and-add scalar multiplication (~4 k Montgomery products per
+// butterfly; n log n / 2 of them: 0.6 s at n = 2^20 -- a one-off per SRS, like the window table).  With it a polynomial
+// given by its EVALUATIONS on H is committed directly: commit(lagrange_srs, evals) == commit(srs, iNTT(evals)).
+// ---------------------------------------------------------------------------------------------
+__device__ G1XYZZ g1_scalar_mul(const G1XYZZ& p, const Fr& k_std) {
+    // k_std: standard-form integer < r.  MSB-first double-and-add; real loops around noinline-sized bodies
+    G1XYZZ acc = xyzz_inf();
+    int top = 7;
+    while (top >= 0 && k_std.l[top] == 0) top--;
+    if (top < 0 || xyzz_is_inf(p)) return acc;
+#pragma unroll 1
+    for (int limb = top; limb >= 0; limb--) {
+        const uint32_t w = k_std.l[limb];
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; bit--) {
+            acc = xyzz_dbl(acc);
+            if ((w >> bit) & 1u) xyzz_add(acc, p);
+        }
+    }
+    return acc;
+}
+__global__ void __launch_bounds__(128) g1_lift_kernel(const G1Affine* __restrict__ in, uint64_t n, G1XYZZ* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p;
+    p.x = fp_load<FqP>(&in[i].x);
+    p.y = fp_load<FqP>(&in[i].y);
+    const G1XYZZ v = xyzz_from_affine(p);
+    fp_store(&out[i].x, v.x);
+    fp_store(&out[i].y, v.y);
+    fp_store(&out[i].zz, v.zz);
+    fp_store(&out[i].zzz, v.zzz);
+}
+__device__ __forceinline__ G1XYZZ load_pt(const G1XYZZ* p) {
+    G1XYZZ v;
+    v.x = fp_load<FqP>(&p->x);
+    v.y = fp_load<FqP>(&p->y);
+    v.zz = fp_load<FqP>(&p->zz);
+    v.zzz = fp_load<FqP>(&p->zzz);
+    return v;
+}
+__device__ __forceinline__ void store_pt(G1XYZZ* p, const G1XYZZ& v) {
+    fp_store(&p->x, v.x);
+    fp_store(&p->y, v.y);
+    fp_store(&p->zz, v.zz);
+    fp_store(&p->zzz, v.zzz);
+}
+// one DIF stage of half-size h with the INVERSE twiddles: (a, b) -> (a + b, (a - b) w_{2h}^-j)
+__global__ void __launch_bounds__(128) g1_dif_stage_kernel(G1XYZZ* __restrict__ pts, uint64_t n, uint64_t h, uint32_t log_2h,
+                                                           const Fr* __restrict__ tw_lo, const Fr* __restrict__ tw_hi) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n / 2) return;
+    const uint64_t j = b & (h - 1);
+    const uint64_t i0 = ((b - j) << 1) + j, i1 = i0 + h;
+    G1XYZZ a = load_pt(pts + i0);
+    const G1XYZZ d = load_pt(pts + i1);
+    G1XYZZ s = a;
+    xyzz_add(s, d);
+    G1XYZZ nd = d;
+    nd.y = fp_neg(nd.y);
+    xyzz_add(a, nd);  // a - b
+    if (j != 0) {
+        // w_{2h}^-j = Winv^(j 2^26 / 2h): composite table lookup, then out of Montgomery form
+        const uint32_t e = (uint32_t)(j << (NTT_MAX_LOG - log_2h));
+        Fr w = fp_load<FrP>(tw_hi + (e >> TW_BITS));
+        const uint32_t l = e & (TW_SIZE - 1);
+        if (l) w = fp_mul(w, fp_load<FrP>(tw_lo + l));
+        a = g1_scalar_mul(a, fp_from_mont(w));
+    }
+    store_pt(pts + i0, s);
+    store_pt(pts + i1, a);
+}
+// bit-reversed position -> natural position, times n^-1, to canonical affine
+__global__ void __launch_bounds__(128) g1_unscramble_kernel(const G1XYZZ* __restrict__ pts, uint64_t n, uint32_t log_n, Fr n_inv_std,
+                                                            G1Affine* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t src = log_n ? (__brevll(i) >> (64 - log_n)) : 0;
+    const G1XYZZ v = g1_scalar_mul(load_pt(pts + src), n_inv_std);
+    const G1Affine r = xyzz_to_affine(v);
+    fp_store(&out[i].x, r.x);
+    fp_store(&out[i].y, r.y);
+}
+
 }  // namespace kzg
 
 using namespace kzg;
@@ -202,6 +289,47 @@ int kzg_srs_load_ptau_range(kzg_ctx* ctx, const char* path, uint64_t first, uint
 
 int kzg_srs_load_ptau(kzg_ctx* ctx, const char* path, uint64_t n_points, kzg_srs** out, uint32_t* power_out) {
     return kzg_srs_load_ptau_range(ctx, path, 0, n_points, out, power_out);
+}
+
+// [L_i(tau)]_1, i < 2^n_bits, from the first 2^n_bits monomial points of `srs`
+int kzg_srs_lagrange(kzg_ctx* ctx, kzg_srs* srs, uint32_t n_bits, kzg_srs** out) {
+    kzg::DeviceGuard _dg(ctx);
+    if (!ctx || !srs || !out || n_bits > 24) return KZG_ERR_ARG;
+    const uint64_t n = 1ull << n_bits;
+    if (srs->n < n) return set_err(ctx, KZG_ERR_ARG, "lagrange SRS: not enough monomial points");
+    kzg_srs* s = new kzg_srs();
+    s->n = n;
+    s->power = srs->power;
+    G1XYZZ* work = nullptr;
+    cudaError_t e = cudaMalloc((void**)&s->d, sizeof(G1Affine) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&work, sizeof(G1XYZZ) * n);
+    if (e != cudaSuccess) {
+        cudaFree(s->d);
+        delete s;
+        return set_err(ctx, KZG_ERR_NOMEM, std::string("lagrange SRS allocation failed: ") + cudaGetErrorString(e));
+    }
+    const uint32_t blocks = (uint32_t)((n + 127) / 128);
+    KZG_LAUNCH(ctx, g1_lift_kernel, blocks, 128, 0, srs->d, n, work);
+    for (uint32_t st = 0; st < n_bits; st++) {
+        const uint64_t h = n >> (st + 1);
+        KZG_LAUNCH(ctx, g1_dif_stage_kernel, (uint32_t)((n / 2 + 127) / 128), 128, 0, work, n, h, n_bits - st, ctx->tw_lo[1],
+                   ctx->tw_hi[1]);
+    }
+    Fr nn = fp_zero<FrP>();
+    nn.l[0] = (uint32_t)n;
+    nn.l[1] = (uint32_t)(n >> 32);
+    const Fr n_inv_std = fp_from_mont(fp_inv(fp_to_mont(nn)));
+    KZG_LAUNCH(ctx, g1_unscramble_kernel, blocks, 128, 0, work, n, n_bits, n_inv_std, s->d);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(work);
+    if (e != cudaSuccess) {
+        cudaFree(s->d);
+        delete s;
+        return set_err(ctx, KZG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = s;
+    return KZG_OK;
 }
 
 int kzg_srs_generate(kzg_ctx* ctx, const uint8_t tau_std[32], uint64_t n_points, kzg_srs** out) {
