@@ -350,3 +350,28 @@ def test_prover_replaces_evals_by_montgomery_form(curve, tau, ptau_factory):
         assert ef.tobytes() == bn.fr_vec_to_mont_bytes(c)
         assert et.tobytes() == bn.fr_vec_to_mont_bytes(inputs.rotate_right(c))
         assert ef.length() == n and ef.getEvaluation(3) == bn.fr_to_mont_bytes(c[3])
+
+
+@pytest.mark.parametrize("kind", ["gs", "gp"])
+def test_batched_verification_on_device(kind, curve, tau, ptau_factory):
+    """m proofs, one device MSM per side of the pairing check over all their commitments, ONE pairing
+    product.  24 honest proofs of mixed shapes are accepted; one bad proof anywhere makes the batch fail; the verdict
+    agrees with the sequential drop-in verifier on every member."""
+    from kzg_grandsums_study_b200.grandsum import mset_eq_kzg_grandsum_verifier_batch
+    from kzg_grandsums_study_b200.grandproduct import mset_eq_kzg_grandproduct_verifier_batch
+    batch_verify = mset_eq_kzg_grandsum_verifier_batch if kind == "gs" else mset_eq_kzg_grandproduct_verifier_batch
+    nbits = 5
+    proofs = []
+    for j in range(24):
+        k = 1 + j % 3
+        got, _, _, _ = run_both(kind, curve, tau, ptau_factory, seed=900 + j, nbits=nbits, k=k, selected=(j % 4 == 3))
+        proofs.append(got)
+    path = run_both.last_path
+    before = curve.launch_count()
+    assert batch_verify(path, proofs, nbits) is True
+    assert curve.launch_count() > before          # the group arithmetic ran on the device
+    assert package_verify(kind, proofs[7], nbits) is True
+    bad = [{"commitments": dict(p["commitments"]), "evaluations": dict(p["evaluations"])} for p in proofs]
+    bad[17]["commitments"]["Q"] = bn.g1_to_bytes(bn.g1_mul_gen(5))
+    assert batch_verify(path, bad, nbits) is False
+    assert package_verify(kind, bad[17], nbits) is False

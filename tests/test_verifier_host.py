@@ -90,3 +90,54 @@ def test_verifier_refuses_non_canonical_and_incomplete_proofs():
         assert hb.g1_from_bytes(shifted) == hb.g1_from_bytes(g)
         assert not hb.g1_bytes_canonical(shifted)
     assert not hb.g1_bytes_canonical(b"\xff" * 64)
+
+
+def _host_msm(bases, scalars):
+    """a host multi-scalar multiplication for the CPU test of the batching logic (the product uses the device MSM)"""
+    from kzg_grandsums_study_b200 import host_bn254 as hb
+    acc = None
+    for i in range(len(scalars) // 32):
+        P = hb.g1_from_bytes(bases[64 * i:64 * i + 64])
+        k = int.from_bytes(scalars[32 * i:32 * i + 32], "little")
+        acc = hb.g1_add(acc, hb.g1_mul(P, k))
+    return hb.g1_to_bytes(acc)
+
+
+@pytest.mark.parametrize("kind", ["gs", "gp"])
+def test_batch_verifier_logic(kind, tmp_path, lib_path):
+    """the linear forms of verify_batch reproduce the sequential verifier: a batch of honest proofs of different shapes
+    (plain, vector, selected) is accepted, the same batch with ONE tampered proof anywhere is rejected, and the single
+    linear forms give the same pairing inputs as steps 6-9 of verify()"""
+    from kzg_grandsums_study_b200 import _verifier_common as vc, host_bn254 as hb
+    nbits = 3
+    n = 1 << nbits
+    tau = inputs.tau_from_seed(777)
+    path = str(tmp_path / "b.ptau")
+    opt.write_ptau(path, nbits, tau)
+    prover = pr.grandsum_prover if kind == "gs" else pr.grandproduct_prover
+    one, zero = bn.fr_to_mont_bytes(1), bytes(32)
+    proofs = []
+    for k, selected in ((1, False), (3, False), (2, True), (1, True)):
+        cols_f = [inputs.random_column(300 + 10 * k + i, n) for i in range(k)]
+        cols_t = [inputs.rotate_right(c) for c in cols_f]
+        sel = (one * (n - 1) + zero, zero + one * (n - 1)) if selected else (None, None)
+        proofs.append(prover(pr.Srs(path, 2 * n), [bn.fr_vec_to_std_bytes(c) for c in cols_f],
+                             [bn.fr_vec_to_std_bytes(c) for c in cols_t], sel[0], sel[1]))
+    # single proofs through the linear forms == the sequential verifier's verdict
+    for proof in proofs:
+        assert vc.verify(kind, path, proof, nbits) is True
+        assert vc.verify_batch(kind, path, [proof], nbits, msm=_host_msm) is True
+    assert vc.verify_batch(kind, path, proofs, nbits, msm=_host_msm) is True
+    assert vc.verify_batch(kind, path, [], nbits, msm=_host_msm) is True
+    for bad_at in range(len(proofs)):
+        batch = [{"commitments": dict(p["commitments"]), "evaluations": dict(p["evaluations"])} for p in proofs]
+        key = list(batch[bad_at]["evaluations"])[-1]
+        good = batch[bad_at]["evaluations"][key]
+        batch[bad_at]["evaluations"][key] = bn.fr_to_mont_bytes((bn.fr_from_mont_bytes(good) + 1) % bn.R)
+        assert vc.verify_batch(kind, path, batch, nbits, msm=_host_msm) is False, bad_at
+        batch[bad_at]["evaluations"][key] = good
+        batch[bad_at]["commitments"]["Wxi"] = bn.g1_to_bytes(bn.g1_mul_gen(11 + bad_at))
+        assert vc.verify_batch(kind, path, batch, nbits, msm=_host_msm) is False, bad_at
+    # malformed member: refused without raising
+    batch = [proofs[0], {"commitments": {}, "evaluations": {}}]
+    assert vc.verify_batch(kind, path, batch, nbits, msm=_host_msm) is False
