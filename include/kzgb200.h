@@ -237,6 +237,8 @@ int kzg_prover_round5(kzg_prover* p, const uint8_t v[32], uint8_t out_w[128]);
  * device vector (ownership moves; free with kzg_buf_free).  The reference REPLACES evalsFs[i].eval / evalsTs[i].eval
  * by their Montgomery form as a side effect of proving (prover.js:147-148); the host layer reproduces that with this. */
 int kzg_prover_take_evals(kzg_prover* p, uint32_t column, int which, kzg_buf** out);
+/* message of the last failed round call (kzg_last_error of the prover's context) */
+const char* kzg_prover_last_error(kzg_prover* p);
 /* number of evaluations / commitments round 4 / round 1 write */
 uint32_t kzg_prover_n_evals(kzg_prover* p);
 uint32_t kzg_prover_n_round1_commitments(kzg_prover* p);

@@ -106,6 +106,7 @@ SIGNATURES = {
     "kzg_prover_round4": (i32, [vp, vp, vp]),
     "kzg_prover_round5": (i32, [vp, vp, vp]),
     "kzg_prover_take_evals": (i32, [vp, u32, i32, C.POINTER(vp)]),
+    "kzg_prover_last_error": (C.c_char_p, [vp]),
     "kzg_prover_n_evals": (u32, [vp]),
     "kzg_prover_n_round1_commitments": (u32, [vp]),
     "kzg_keccak256": (None, [vp, C.c_size_t, vp]),

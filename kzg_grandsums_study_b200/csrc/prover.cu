@@ -175,6 +175,9 @@ static uint32_t log2u(uint64_t n) {
 
 extern "C" {
 
+const char* kzg_prover_last_error(kzg_prover* p) {
+    return p ? kzg_last_error(p->ctx) : "null prover";
+}
 uint32_t kzg_prover_n_evals(kzg_prover* p) {
     kzg::DeviceGuard _dg(p ? p->ctx : nullptr);
     if (!p) return 0;
