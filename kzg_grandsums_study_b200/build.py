@@ -18,6 +18,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
+if os.environ.get("KZGB200_DEBUG_BOUNDS") == "1":
+    # debug build: every hand-computed index of the MSM kernels is checked (msm.cu KZG_IDX_OK); slower, lanes serialised
+    NVCC_FLAGS.append("-DKZG_BOUNDS_CHECK")
 
 
 def _nvcc():

@@ -39,6 +39,35 @@
 namespace kzg {
 
 // ---------------------------------------------------------------------------------------------
+// Debug build (KZGB200_DEBUG_BOUNDS=1 python -m kzg_grandsums_study_b200.build  ->  -DKZG_BOUNDS_CHECK): every
+// hand-computed index of the sort, the affine rounds and the walk -- staged shared-memory slots, scratch-arena offsets,
+// table gathers -- is checked against the limit the host laid the scratch out with; a violation sets a bit in a device
+// word, the access is skipped, and the MSM returns an error naming the site.  (compute-sanitizer is closed on this GPU
+// pool; the whole -m gpu suite has been run once under this build: profiles/r02_bounds_check.md.)  In the normal build
+// KZG_IDX_OK(...) is the constant `true`.
+// ---------------------------------------------------------------------------------------------
+#ifdef KZG_BOUNDS_CHECK
+struct MsmDebugLimits {
+    unsigned long long sorted_entries, mid_entries, partials, prefix_elems, totals, aff_cap[2], table_points, nkeys, dense_in;
+};
+__device__ MsmDebugLimits g_dbg;
+__device__ unsigned int g_dbg_violation;
+__device__ __forceinline__ bool kzg_idx_ok(unsigned long long idx, unsigned long long limit, int site) {
+    if (idx < limit) return true;
+    atomicOr(&g_dbg_violation, 1u << site);
+    return false;
+}
+#define KZG_IDX_OK(idx, limit, site) kzg_idx_ok((unsigned long long)(idx), (unsigned long long)(limit), site)
+#define KZG_DBG(field) (g_dbg.field)
+#else
+#define KZG_IDX_OK(idx, limit, site) true
+#define KZG_DBG(field) 0
+#endif
+enum { DBG_DIGITS_SORTED = 0, DBG_PART_RANK = 1, DBG_PART_STAGE = 2, DBG_PART_MID = 3, DBG_CHUNK_STAGE = 4, DBG_CHUNK_SORTED = 5,
+       DBG_CHUNK_COUNTS = 6, DBG_WALK_PARTIALS = 7, DBG_WALK_GATHER = 8, DBG_FWD_PREFIX = 9, DBG_FWD_GATHER = 10,
+       DBG_BWD_OUT = 11, DBG_BWD_GATHER = 12, DBG_WALK_DENSE = 13, DBG_FWD_TOTALS = 14 };
+
+// ---------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------
 struct MsmGeom {
@@ -120,7 +149,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmJobs jobs, MsmGeom g
         if (valid && lane == leader) base = atomicAdd(&counts_or_cursor[key], (uint32_t)__popc(peers));
         if (SCATTER) {
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (valid) {
+            if (valid && KZG_IDX_OK(base + rank, KZG_DBG(sorted_entries), DBG_DIGITS_SORTED)) {
                 uint32_t entry = table ? (uint32_t)(w * g.stride + i) : (uint32_t)i;
                 // every bucket has ONE partially filled 32-byte sector of `sorted` at any time (2^(c-1) x 32 B in
                 // total): ask L2 to keep those lines until their other 7 entries arrive
@@ -550,7 +579,9 @@ __global__ void __launch_bounds__(PART_THREADS, 2) msm_part_scatter_kernel(MsmJo
             sc[k] = load_scalar_stream(scalars, i, montgomery);
             uint32_t slot = local * g.nwin;  // one slot per (scalar, window)
             msm_for_digits(sc[k], g, key_base, i, [&](uint32_t key, uint32_t) {
-                ranks[slot++] = (uint16_t)atomicAdd(&hist[key >> sg.low_bits], 1u);
+                const uint16_t rk = (uint16_t)atomicAdd(&hist[key >> sg.low_bits], 1u);
+                if (KZG_IDX_OK(slot, PART_TILE_ENTRIES, DBG_PART_RANK)) ranks[slot] = rk;
+                slot++;
             });
         }
     }
@@ -568,7 +599,8 @@ __global__ void __launch_bounds__(PART_THREADS, 2) msm_part_scatter_kernel(MsmJo
         if (i < last) {
             uint32_t slot = local * g.nwin;
             msm_for_digits(sc[k], g, key_base, i, [&](uint32_t key, uint32_t entry) {
-                stage[loff[key >> sg.low_bits] + ranks[slot++]] = make_uint2(entry, key);
+                const uint32_t at = loff[key >> sg.low_bits] + ranks[slot++];
+                if (KZG_IDX_OK(at, PART_TILE_ENTRIES, DBG_PART_STAGE)) stage[at] = make_uint2(entry, key);
             });
         }
     }
@@ -577,7 +609,7 @@ __global__ void __launch_bounds__(PART_THREADS, 2) msm_part_scatter_kernel(MsmJo
     for (uint32_t sidx = threadIdx.x; sidx < total; sidx += PART_THREADS) {
         const uint2 e = stage[sidx];
         const uint32_t p = e.y >> sg.low_bits;
-        mid[gbase[p] + (sidx - loff[p])] = e;
+        if (KZG_IDX_OK(gbase[p] + (sidx - loff[p]), KZG_DBG(mid_entries), DBG_PART_MID)) mid[gbase[p] + (sidx - loff[p])] = e;
     }
 }
 
@@ -614,7 +646,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS) msm_chunk_hist_kernel(const uin
     uint16_t* keep = chunk_hist + ((size_t)blockIdx.x << sg.low_bits);  // (a chunk holds SORT_CHUNK <= 65535 entries)
     for (uint32_t k = threadIdx.x; k < nlow; k += CHUNK_THREADS) {
         keep[k] = (uint16_t)h[k];
-        if (h[k]) atomicAdd(&dst[k], h[k]);
+        if (h[k] && KZG_IDX_OK(((size_t)part << sg.low_bits) + k, KZG_DBG(nkeys), DBG_CHUNK_COUNTS)) atomicAdd(&dst[k], h[k]);
     }
 }
 
@@ -652,14 +684,16 @@ __global__ void __launch_bounds__(CHUNK_THREADS) msm_chunk_scatter_kernel(const 
         const uint2 v = __ldg(&mid[e]);
         const uint32_t k = v.y & mask;
         const uint32_t slot = loff[k] + atomicAdd(&cnt[k], 1u);
-        stage[slot] = v.x;
-        skey[slot] = (uint16_t)k;
+        if (KZG_IDX_OK(slot, SORT_CHUNK, DBG_CHUNK_STAGE)) {
+            stage[slot] = v.x;
+            skey[slot] = (uint16_t)k;
+        }
     }
     __syncthreads();
     const uint32_t total = end - begin;
     for (uint32_t sidx = threadIdx.x; sidx < total; sidx += CHUNK_THREADS) {
         const uint32_t k = skey[sidx];
-        sorted[base[k] + (sidx - loff[k])] = stage[sidx];
+        if (KZG_IDX_OK(base[k] + (sidx - loff[k]), KZG_DBG(sorted_entries), DBG_CHUNK_SORTED)) sorted[base[k] + (sidx - loff[k])] = stage[sidx];
     }
 }
 
@@ -754,10 +788,17 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
 
     G1XYZZ acc = xyzz_inf();
     uint32_t e = DIRECT ? begin : sorted[begin];
+#ifdef KZG_BOUNDS_CHECK
+    for (uint32_t j = begin; j < end; j++) {  // every operand of the slice, before anything is fetched
+        if (DIRECT ? !KZG_IDX_OK(j, KZG_DBG(dense_in), DBG_WALK_DENSE)
+                   : !KZG_IDX_OK(sorted[j] & 0x7fffffffu, KZG_DBG(table_points), DBG_WALK_GATHER)) return;
+    }
+#endif
     G1Affine p = DIRECT ? load_dense_point(dense_x, dense_y, e) : load_affine_gather(bases + (e & 0x7fffffffu));
     for (uint32_t j = begin; j < end; j++) {
         if (j == key_end) {  // bucket boundary inside the slice
-            store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
+            if (KZG_IDX_OK(pbase[key] + (t - offsets[key] / slice), KZG_DBG(partials), DBG_WALK_PARTIALS))
+                store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
             acc = xyzz_inf();
             do {
                 key++;
@@ -776,7 +817,8 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __r
         e = e_next;
         p = p_next;
     }
-    store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
+    if (KZG_IDX_OK(pbase[key] + (t - offsets[key] / slice), KZG_DBG(partials), DBG_WALK_PARTIALS))
+        store_xyzz(partials + pbase[key] + (t - offsets[key] / slice), acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -823,6 +865,12 @@ __device__ __forceinline__ Fq load_fq_ldg(const Fq* p) {
 // register is where the warp waits)
 template <bool INDEXED>
 __device__ __forceinline__ G1Affine aff_request_point(const AffRound& a, uint32_t h) {
+    if (!(INDEXED ? KZG_IDX_OK(h & 0x7fffffffu, KZG_DBG(table_points), DBG_BWD_GATHER) : KZG_IDX_OK(h, KZG_DBG(dense_in), DBG_BWD_GATHER))) {
+        G1Affine z;
+        z.x = fp_zero<FqP>();
+        z.y = fp_zero<FqP>();
+        return z;
+    }
     if (INDEXED) return load_affine_gather(a.bases + (h & 0x7fffffffu));
     G1Affine p;
     p.x = load_fq_ldg(a.in_x + h);
@@ -913,6 +961,8 @@ __device__ __forceinline__ void aff_step_down(const AffRound& a, AffCursor& c, u
 
 template <bool INDEXED>
 __device__ __forceinline__ Fq aff_load_x(const AffRound& a, uint32_t h) {
+    if (!(INDEXED ? KZG_IDX_OK(h & 0x7fffffffu, KZG_DBG(table_points), DBG_FWD_GATHER) : KZG_IDX_OK(h, KZG_DBG(dense_in), DBG_FWD_GATHER)))
+        return fp_one<FqP>();
     return INDEXED ? load_fq_gather(&(a.bases + (h & 0x7fffffffu))->x) : load_fq_ldg(a.in_x + h);
 }
 
@@ -950,7 +1000,7 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRoun
                     nx2 = aff_load_x<INDEXED>(a, nh2);
                 }
             }
-            if (pair) {
+            if (pair && KZG_IDX_OK((uint64_t)(o - begin) * a.nthreads + t, KZG_DBG(prefix_elems), DBG_FWD_PREFIX)) {
                 Fq d;
                 if (fp_eq(x1, x2) || fp_is_zero(x1) || fp_is_zero(x2)) {  // exceptional: decide on the full points
                     const G1Affine p1 = aff_load_point<INDEXED>(a, h1), p2 = aff_load_point<INDEXED>(a, h2);
@@ -968,7 +1018,7 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_forward_kernel(AffRoun
             x2 = nx2;
         }
     }
-    fp_store(totals + t, acc);
+    if (KZG_IDX_OK(t, KZG_DBG(totals), DBG_FWD_TOTALS)) fp_store(totals + t, acc);
 }
 
 template <bool INDEXED>
@@ -1042,8 +1092,10 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRou
                 r.y = fp_zero<FqP>();
             }
         }
-        fp_store(out_x + o, r.x);
-        fp_store(out_y + o, r.y);
+        if (KZG_IDX_OK(o, KZG_DBG(aff_cap[0]), DBG_BWD_OUT)) {
+            fp_store(out_x + o, r.x);
+            fp_store(out_y + o, r.y);
+        }
         if (!more) break;
         p1 = n1;
         p2 = n2;
@@ -1709,6 +1761,23 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
     uint16_t* chunk_hist = (uint16_t*)(sc + o_chist);
 
     const G1Affine* pts = bases.table ? bases.table : bases.pts;
+#ifdef KZG_BOUNDS_CHECK
+    MsmDebugLimits lim;
+    memset(&lim, 0, sizeof(lim));
+    {
+        KZG_CUDA(ctx, cudaDeviceSynchronize());  // the limits are one device global: debug builds run the lanes one after the other
+        lim.sorted_entries = max_entries;
+        lim.mid_entries = max_entries;
+        lim.partials = max_parts;
+        lim.prefix_elems = aff_rounds ? ((aff_entries[1] + aff_m - 1) / aff_m) * aff_m : 0;
+        lim.totals = aff_rounds ? (aff_entries[1] + aff_m - 1) / aff_m : 0;
+        lim.table_points = bases.table ? (uint64_t)(g.nwin - 1) * g.stride + n : n;
+        lim.nkeys = nkeys;
+        const unsigned int zero = 0;
+        KZG_CUDA(ctx, cudaMemcpyToSymbol(g_dbg, &lim, sizeof(lim)));
+        KZG_CUDA(ctx, cudaMemcpyToSymbol(g_dbg_violation, &zero, sizeof(zero)));
+    }
+#endif
     KZG_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nkeys + 1), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(heavy, 0, sizeof(uint32_t), ctx->stream));
     KZG_CUDA(ctx, cudaMemsetAsync(multi, 0, sizeof(uint32_t), ctx->stream));
@@ -1770,6 +1839,12 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
         ar.off_out = off_out;
         ar.nkeys = nkeys;
         ar.nthreads = (uint32_t)((aff_entries[r] + aff_m - 1) / aff_m);
+#ifdef KZG_BOUNDS_CHECK
+        KZG_CUDA(ctx, cudaDeviceSynchronize());
+        lim.aff_cap[0] = aff_entries[r];                       // what this round may write
+        lim.dense_in = r == 1 ? 0 : aff_entries[r - 1];        // what it may read from the previous round's list
+        KZG_CUDA(ctx, cudaMemcpyToSymbol(g_dbg, &lim, sizeof(lim)));
+#endif
         // Chunks of threads, a multiple of the block size each, alternating between the lane's main stream and its side
         // stream: consecutive kernels of ONE stream do not overlap, so with all chunks on one stream every chunk would
         // expose its own tail (a block lives ~90 us: measured +1.6 ms at 2^24 points with 4 chunks per round); on two
@@ -1872,6 +1947,11 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
     KZG_LAUNCH(ctx, msm_scan_apply_kernel, ntiles, SCAN_THREADS, 0, 1, counts, walk_offsets, nkeys, g.seg, aff_rounds, tile_sums,
                segoff, cursor, heavy + 1, heavy, multi + 1, multi, huge + 1, huge);
     const uint32_t ablocks = (uint32_t)((max_tasks + 127) / 128);
+#ifdef KZG_BOUNDS_CHECK
+    KZG_CUDA(ctx, cudaDeviceSynchronize());
+    lim.dense_in = aff_rounds ? aff_entries[aff_rounds] : 0;
+    KZG_CUDA(ctx, cudaMemcpyToSymbol(g_dbg, &lim, sizeof(lim)));
+#endif
     timed_begin(ctx, KZG_TIMED_MSM_ACCUMULATE);
     if (aff_rounds)
         KZG_LAUNCH(ctx, msm_accumulate_kernel<true>, ablocks, 128, 0, (const G1Affine*)nullptr, walk_x, walk_y,
@@ -1913,6 +1993,18 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
     if (!g.table) KZG_LAUNCH(ctx, msm_horner_kernel, 1, 32, 0, set_sums, g.nwin, g.c, results);
     timed_end(ctx, KZG_TIMED_MSM_REDUCE);
     KZG_CHECK_LAUNCH(ctx);
+#ifdef KZG_BOUNDS_CHECK
+    {
+        KZG_CUDA(ctx, cudaDeviceSynchronize());
+        unsigned int bad = 0;
+        KZG_CUDA(ctx, cudaMemcpyFromSymbol(&bad, g_dbg_violation, sizeof(bad)));
+        if (bad) {
+            char msg[128];
+            snprintf(msg, sizeof(msg), "msm: out-of-bounds index caught by the debug build, site mask 0x%x (enum DBG_* in msm.cu)", bad);
+            return set_err(ctx, KZG_ERR_CUDA, msg);
+        }
+    }
+#endif
     return KZG_OK;
 }
 

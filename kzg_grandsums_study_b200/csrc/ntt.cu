@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_last_pass_kernel(const Fr*
     const uint64_t mid = blockIdx.x % M;
     const uint64_t k1_0 = (blockIdx.x / M) * T;
     const uint32_t log_s1 = plan.log_n - plan.radbits[0];  // S_1 = N / R_1   (only used when P > 1)
+    // (element index fastest: the warp reads 1 KiB of one contiguous row.  Row index fastest -- conflict-free shared
+    // stores, 128-byte global segments -- was measured: 47 M instead of 67 M bank conflicts, but 1.086 vs 1.046 ms)
     for (uint32_t idx = threadIdx.x; idx < R * T; idx += blockDim.x) {
         uint32_t n = idx % R, r = idx / R;
         uint64_t gi = (P > 1 ? ((k1_0 + r) << log_s1) : 0) + (mid << rbits) + n;

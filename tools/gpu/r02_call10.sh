@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 2400 python -m pytest tests -x -q -m gpu --deselect tests/test_gpu_large_parity.py ) > gpurun_out/r02_c10_tests.log 2>&1
+tail -6 gpurun_out/r02_c10_tests.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_c10_bench.json 2> gpurun_out/r02_c10_bench.err; tail -3 gpurun_out/r02_c10_bench.err
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_fmaheavy.sum,smsp__thread_inst_executed_per_inst_executed.ratio
+timeout 900 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r02_msm24_launches.csv python tools/msm_once.py 24 0 2 > gpurun_out/r02_c10_ncu24.log 2>&1
+timeout 600 ncu --metrics $M --clock-control none -k regex:ntt_ --csv --log-file gpurun_out/r02_ntt24_launches.csv python tools/ntt_once.py 24 1 > gpurun_out/r02_c10_ncu_ntt.log 2>&1
+timeout 600 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r02_msm21_launches.csv python tools/msm_once.py 21 0 2 > gpurun_out/r02_c10_ncu21.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_prove20_launches.csv python tools/prove_once.py 20 gs 2 > gpurun_out/r02_c10_ncu_prove.log 2>&1
+echo done

@@ -43,7 +43,7 @@ def launches(path, out, title, last_n=None):
         f.write("```\n")
 
 
-def multi(path, out, title, first_kernel):
+def multi(path, out, title, first_kernel, take=""):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     ix = {h: i for i, h in enumerate(rows[0])}
     data = collections.OrderedDict()
@@ -52,7 +52,7 @@ def multi(path, out, title, first_kernel):
         data.setdefault((int(r[ix["ID"]]), name), {})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
     items = list(data.items())
     starts = [i for i, ((_, k), _m) in enumerate(items) if k.startswith(first_kernel)]
-    seq = items[starts[-1]:]
+    seq = items[starts[0]:starts[0] + int(take)] if take else items[starts[-1]:]
     T, RD, WR, FM = "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", \
         "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"
     total = sum(m[T] for _, m in seq) / 1e6
@@ -79,7 +79,7 @@ def multi(path, out, title, first_kernel):
         f.write("```\n")
 
 
-def traffic(path, key, first_kernel, pattern, family, note=""):
+def traffic(path, key, first_kernel, pattern, family, note="", take=""):
     import json
     import os
     import re
@@ -93,7 +93,7 @@ def traffic(path, key, first_kernel, pattern, family, note=""):
         data.setdefault((int(r[ix["ID"]]), name), {})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
     items = list(data.items())
     starts = [i for i, ((_, k), _m) in enumerate(items) if k.startswith(first_kernel)]
-    seq = items[starts[-1]:]
+    seq = items[starts[0]:starts[0] + int(take)] if take else items[starts[-1]:]   # take = N: the first N launches from the first start
     rx = re.compile(pattern)
     sel = [(k, m) for (_, k), m in seq if rx.search(k)]
     dram = sum(m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"] for _, m in sel)
@@ -149,7 +149,7 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "traffic":
     traffic(*sys.argv[2:])
     sys.exit(0)
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "multi":
-    multi(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
+    multi(*sys.argv[2:])
     sys.exit(0)
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
