@@ -1599,7 +1599,7 @@ static uint32_t msm_affine_rounds(kzg_ctx* ctx, uint64_t max_entries, uint32_t n
 
 // an event for stream-to-stream ordering inside one call, from a per-context ring (no timing, never destroyed before
 // the context is): a wait captures the state of the event when it is enqueued, so a slot can be re-recorded later
-static cudaEvent_t order_event(kzg_ctx* ctx) {
+cudaEvent_t order_event(kzg_ctx* ctx) {
     if (ctx->order_events.size() < 256) {
         cudaEvent_t e = nullptr;
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);

@@ -134,7 +134,7 @@ def test_affine_round_chunking(curve, tau, chunks):
 
 @pytest.mark.parametrize("log_n", [12, 22])
 def test_host_partial_equals_resident_partial(curve, tau, log_n):
-    """kzg_srs_msm_host_partial (scalars in host memory, piecewise upload from 2^22 points on) leaves the same group
+    """kzg_srs_msm_host_partial (scalars in host memory, piecewise upload from 2^21 points on) leaves the same group
     element as kzg_srs_msm_partial; combined with a second shard it gives the closed form of the whole MSM"""
     import torch
     from kzg_grandsums_study_b200 import synthetic
