@@ -447,7 +447,7 @@ def run_b200(args):
                        "srs_precompute_ms": srs_precompute_ms,
                        "table_bytes": 64 * shard * geom["windows"] if not args.window else 0, "host_cores": os.cpu_count(),
                        "l2": "256 MiB buffer rewritten between timed iterations; inputs (1.5 GiB) exceed L2",
-                       "known_answer_ok": check},
+                       "known_answer_ok": check, "result_affine_hex": result_resident.hex()},
             "e2e": {"value": N / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * shard, "d2h_bytes_per_step": 64},
             "gpu_launches": int(launches),
