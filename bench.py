@@ -511,10 +511,10 @@ def bench_ntt(curve, log_n, hbm_peak, peak_kind, imad_peak):
                 best[inverse] = t if best[inverse] is None else min(best[inverse], t)
     ms = best[0]
     counted = ncu_counted("ntt_2_%d" % log_n, "ntt")
-    # model: per pass ~3 products per element in the butterflies (trivial twiddles skipped by whole warps), 2 at the
-    # first pass boundary (hi x lo composite twiddle), 1 at the others (mid table); N^-1 rides on the first boundary
+    # model: per pass ~3 products per element in the butterflies (trivial twiddles skipped by whole warps), 1 at every pass
+    # boundary (direct twiddle tables; N^-1 of an inverse transform rides on the last one)
     passes = (log_n + 7) // 8
-    modelled = n * (3.0 * passes + 2 + max(0, passes - 2)) * 128
+    modelled = n * (3.0 * passes + (passes - 1)) * 128
     executed = counted["fmaheavy_thread_instructions"] if counted else modelled
     rate = executed / (ms * 1e-3)
     return {"bound": "imad", "kernel": "ntt_strided_pass_kernel x%d + ntt_last_pass_kernel (one 2^%d transform)" % (passes - 1, log_n),

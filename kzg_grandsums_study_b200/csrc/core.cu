@@ -32,6 +32,7 @@ int ctx_set_option(kzg_ctx* ctx, const char* name, long long value) {
     else if (k == "msm_merge") t.merge = reset ? def.merge : (int)value;
     else if (k == "timeline") t.timeline = reset ? 0 : (int)value;
     else if (k == "ntt_tile") t.ntt_tile = reset ? def.ntt_tile : (int)value;
+    else if (k == "ntt_big_table") t.ntt_big_table = reset ? def.ntt_big_table : (int)value;
     else return set_err(ctx, KZG_ERR_ARG, "unknown option: " + k);
     return KZG_OK;
 }
@@ -289,7 +290,7 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
     // the tuning knobs, read once (kzg_ctx_set_option changes them later)
     static const char* const knobs[] = {"aff_rounds", "aff_m", "aff_chunks", "aff_min_entries_log", "aff_min_left_log",
                                         "aff_min_fill", "part_sort", "red_k0", "tail_width", "host_piece_min_log",
-                                        "split_min_log", "split_max_log", "msm_merge", "timeline", "ntt_tile"};
+                                        "split_min_log", "split_max_log", "msm_merge", "timeline", "ntt_tile", "ntt_big_table"};
     for (const char* k : knobs) {
         std::string env = "KZGB200_";
         for (const char* c = k; *c; c++) env += (char)toupper(*c);
@@ -345,7 +346,8 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
         cudaFree(ctx->tw_hi[d]);
         cudaFree(ctx->tw_mid[d]);
     }
-    for (auto* t : ctx->tw_hi_scaled) cudaFree(t);
+    for (auto* t : ctx->tw_mid_scaled) cudaFree(t);
+    for (auto* t : ctx->tw_big) cudaFree(t);
     for (int tag = 0; tag < KZG_TIMED_TAGS; tag++)
         for (auto& pr : ctx->timed[tag]) {
             cudaEventDestroy(pr.first);

@@ -11,8 +11,8 @@
 // at a time in registers, 128-bit shared-memory accesses), multiplies by the inter-pass twiddle
 // w_{N_i}^{k_i * column} and writes back; the last pass works on contiguous rows and scatters T-wide contiguous
 // runs into natural order.  Every element therefore crosses HBM once per pass (P reads + P writes); the arithmetic
-// (~3 products per element and pass in the butterflies, 2 at the first pass boundary, 1 at the others; N^-1 of an
-// inverse transform rides on the first boundary's table) is what bounds it on B200 -- see DESIGN.md.
+// (~3 products per element and pass in the butterflies, 1 at every pass boundary; N^-1 of an inverse transform rides
+// on the last boundary's table) is what bounds it on B200 -- see DESIGN.md.
 //
 // Twiddles come from two 8192-entry tables per direction, W = w_{2^26}: lo[i] = W^i, hi[j] = W^(8192 j): every
 // twiddle of a transform of size <= 2^26 is hi[.] or hi[.] * lo[.]; plus mid[e] = w_{2^16}^e (2 MB) so that every
@@ -142,15 +142,21 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
 // The tile -- R rows of T * 32 = 256 contiguous bytes, S elements apart -- is staged in shared memory by the TMA unit:
 // thread n issues ONE bulk copy for row n and the block waits on an mbarrier for the R * 256 bytes; rows beyond the
 // valid input (zero-padded transforms, Evaluations.fromPolynomial with an extension) are zero-filled by the threads.
-// Inter-pass twiddle w_{N_i}^(k * column), N_i = R * S: one product with the 2^16-entry `mid` table when N_i <= 2^16,
-// the hi x lo composite otherwise; `scaled` (inverse transforms, first pass): the hi table carries the factor N^-1.
+// Inter-pass twiddle w_{N_i}^(k * column), N_i = R * S -- ONE product per element whenever a direct table covers N_i:
+//   tw_mode 0: table[e << tw_shift]: `mid` (w_{2^16}^e, 2 MB, L2-resident) for N_i <= 2^16 -- for an inverse transform the
+//              copy of `mid` scaled by N^-1 on the LAST strided pass, so that the scaling costs nothing --, `big`
+//              (w_{2^24}^e, 512 MB of HBM per direction, built on first use) for 2^17 <= N_i <= 2^24: one random 32-byte
+//              gather per element, whose sectors the block asks the L2 for (prefetch.global.L2) before it starts its
+//              butterflies -- the pass is bound by the integer pipe, the memory system has the room;
+//   tw_mode 1: the hi x lo composite (two products), transforms above 2^24 only.
+// `always`: the table carries a scale factor, so e = 0 is not a shortcut.
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_strided_pass_kernel(const Fr* __restrict__ src, uint64_t n_in,
                                                                        Fr* __restrict__ dst, uint32_t rbits, uint32_t T,
-                                                                       uint32_t log_stride, uint32_t use_mid, uint32_t scaled,
+                                                                       uint32_t log_stride, uint32_t tw_mode, uint32_t tw_shift,
+                                                                       uint32_t always, uint32_t prefetch,
                                                                        const Fr* __restrict__ tw_lo,
-                                                                       const Fr* __restrict__ tw_hi_butterfly,
-                                                                       const Fr* __restrict__ tw_hi_boundary,
-                                                                       const Fr* __restrict__ tw_mid) {
+                                                                       const Fr* __restrict__ tw_hi,
+                                                                       const Fr* __restrict__ tw_table) {
     extern __shared__ uint4 smem_raw[];
     Fr* sh = reinterpret_cast<Fr*>(smem_raw);
     __shared__ __align__(8) uint64_t bar;
@@ -182,23 +188,30 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_strided_pass_kernel(const 
             }
         }
     }
-    smem_twiddles(tw, rbits, tw_hi_butterfly);
+    smem_twiddles(tw, rbits, tw_hi);
+    const uint32_t log_ni = rbits + log_stride;
+    if (prefetch) {  // the boundary twiddles of this tile: 2048 scattered sectors of the big table, wanted ~50 us from now
+        for (uint32_t idx = threadIdx.x; idx < R * T; idx += blockDim.x) {
+            const uint32_t c = idx % T, k = bitrev(idx / T, rbits);
+            const uint64_t e = ((uint64_t)k * (c0 + c)) & ((1ull << log_ni) - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tw_table + (e << tw_shift)));
+        }
+    }
     mbar_wait(&bar, 0);
     __syncthreads();
     smem_dif(sh, rbits, T, tw);
-    // twiddle w_{N_i}^{k * col}, N_i = R * S : exponent in units of W = w_{2^26}
-    const uint32_t log_ni = rbits + log_stride;
-    const uint32_t shift = NTT_MAX_LOG - log_ni;
+    // twiddle w_{N_i}^{k * col}, N_i = R * S
+    const uint32_t shift = NTT_MAX_LOG - log_ni;  // composite mode: exponent in units of W = w_{2^26}
+#pragma unroll 2
     for (uint32_t idx = threadIdx.x; idx < R * T; idx += blockDim.x) {
         uint32_t c = idx % T, p = idx / T;
         uint32_t k = bitrev(p, rbits);
         Fr v = fp_load<FrP>(sh + idx);
         uint64_t col = c0 + c;
         uint64_t e = ((uint64_t)k * col) & ((1ull << log_ni) - 1);
-        if (use_mid) {
-            if (e != 0) v = fp_mul(v, fp_load<FrP>(tw_mid + (e << (16 - log_ni))));
-        } else if (scaled || e != 0) {
-            v = fp_mul(v, tw_lookup(tw_lo, tw_hi_boundary, (uint32_t)(e << shift)));
+        if (always || e != 0) {
+            if (tw_mode == 0) v = fp_mul(v, fp_load<FrP>(tw_table + (e << tw_shift)));
+            else v = fp_mul(v, tw_lookup(tw_lo, tw_hi, (uint32_t)(e << shift)));
         }
         fp_store(dst + base + (uint64_t)k * S + c, v);
     }
@@ -317,9 +330,18 @@ __global__ void tw_mid_kernel(Fr* __restrict__ mid, const Fr* __restrict__ lo, c
     if (l) v = fp_mul(v, fp_load<FrP>(lo + l));
     fp_store(mid + e, v);
 }
-__global__ void tw_scale_kernel(Fr* __restrict__ out, const Fr* __restrict__ in, Fr scale) {
+__global__ void tw_scale_kernel(Fr* __restrict__ out, const Fr* __restrict__ in, Fr scale, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < TW_SIZE) fp_store(out + i, fp_mul(fp_load<FrP>(in + i), scale));
+    if (i < count) fp_store(out + i, fp_mul(fp_load<FrP>(in + i), scale));
+}
+// big[e] = W^(4 e) = w_{2^24}^e, e < 2^24
+__global__ void tw_big_kernel(Fr* __restrict__ big, const Fr* __restrict__ lo, const Fr* __restrict__ hi) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t x = e << 2;
+    Fr v = fp_load<FrP>(hi + (x >> TW_BITS));
+    const uint32_t l = x & (TW_SIZE - 1);
+    if (l) v = fp_mul(v, fp_load<FrP>(lo + l));
+    fp_store(big + e, v);
 }
 
 int ntt_init_tables(kzg_ctx* ctx) {
@@ -337,18 +359,38 @@ int ntt_init_tables(kzg_ctx* ctx) {
     return KZG_OK;
 }
 
-// inverse transforms of 2^log_n points: the hi table of the inverse direction times N^-1 (built on first use, 256 KB)
-static int ntt_scaled_hi(kzg_ctx* ctx, uint32_t log_n, const Fr** out) {
-    if (!ctx->tw_hi_scaled[log_n]) {
+// inverse transforms of 2^log_n points: the `mid` table of the inverse direction times N^-1 (built on first use, 2 MB);
+// the last strided pass of a transform always has N_i <= 2^16, so the scaling rides on it for free
+static int ntt_scaled_mid(kzg_ctx* ctx, uint32_t log_n, const Fr** out) {
+    if (!ctx->tw_mid_scaled[log_n]) {
         Fr* t = nullptr;
-        KZG_CUDA(ctx, cudaMalloc((void**)&t, sizeof(Fr) * TW_SIZE));
+        KZG_CUDA(ctx, cudaMalloc((void**)&t, sizeof(Fr) << 16));
         const Fr scale = fp_inv(fr_from_u64_host(1ull << log_n));
-        KZG_LAUNCH(ctx, tw_scale_kernel, TW_SIZE / 256, 256, 0, t, ctx->tw_hi[1], scale);
+        KZG_LAUNCH(ctx, tw_scale_kernel, (1u << 16) / 256, 256, 0, t, ctx->tw_mid[1], scale, 1u << 16);
         KZG_CHECK_LAUNCH(ctx);
         KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // one-off: the other lane's stream may use the table next
-        ctx->tw_hi_scaled[log_n] = t;
+        ctx->tw_mid_scaled[log_n] = t;
     }
-    *out = ctx->tw_hi_scaled[log_n];
+    *out = ctx->tw_mid_scaled[log_n];
+    return KZG_OK;
+}
+// w_{2^24}^e for every e: the first boundary of a transform of 2^17 .. 2^24 points in ONE product (512 MB per direction:
+// HBM capacity spent to delete a product per element, like the MSM's window table)
+static int ntt_big_table(kzg_ctx* ctx, int dir, const Fr** out) {
+    if (!ctx->tw_big[dir]) {
+        Fr* t = nullptr;
+        cudaError_t e = cudaMalloc((void**)&t, sizeof(Fr) << 24);
+        if (e != cudaSuccess) {  // no room: the composite twiddles still work
+            cudaGetLastError();
+            *out = nullptr;
+            return KZG_OK;
+        }
+        KZG_LAUNCH(ctx, tw_big_kernel, (1u << 24) / 256, 256, 0, t, ctx->tw_lo[dir], ctx->tw_hi[dir]);
+        KZG_CHECK_LAUNCH(ctx);
+        KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->tw_big[dir] = t;
+    }
+    *out = ctx->tw_big[dir];
     return KZG_OK;
 }
 
@@ -383,8 +425,12 @@ int ntt_run(kzg_ctx* ctx, const Fr* in, uint64_t n_in, Fr* out, uint32_t log_n, 
         KZG_CHECK_LAUNCH(ctx);
         return KZG_OK;
     }
-    const Fr* hi_scaled = nullptr;
-    if (inverse) KZG_TRY(ntt_scaled_hi(ctx, log_n, &hi_scaled));  // (the first pass applies N^-1 with its twiddles)
+    const Fr* mid_scaled = nullptr;
+    if (inverse) KZG_TRY(ntt_scaled_mid(ctx, log_n, &mid_scaled));  // (the last strided pass applies N^-1 with its twiddles)
+    const Fr* big = nullptr;
+    // (measured: 3.58 vs 3.75 ms at 2^24, 0.434 vs 0.450 at 2^21, but 0.258 vs 0.250 at 2^20 -- sparse use of the table's lines)
+    if (log_n >= (ctx->tuning.ntt_big_table > 1 ? 17u : 21u) && log_n <= 24 && ctx->tuning.ntt_big_table)
+        KZG_TRY(ntt_big_table(ctx, dir, &big));
     Fr* tmp = nullptr;
     KZG_CUDA(ctx, cudaMallocAsync((void**)&tmp, sizeof(Fr) * N, ctx->stream));
     // tile width T (columns = contiguous elements per row) and threads per block: one thread per two radix-4 butterflies
@@ -399,14 +445,25 @@ int ntt_run(kzg_ctx* ctx, const Fr* in, uint64_t n_in, Fr* out, uint32_t log_n, 
         log_stride -= rb;
         const uint32_t R = 1u << rb;
         const uint32_t grid = (uint32_t)(N / ((uint64_t)R * T));
-        const uint32_t scaled = inverse && i == 0 ? 1u : 0u;
-        const uint32_t use_mid = !scaled && log_ni <= 16 ? 1u : 0u;
+        const bool last_strided = i + 2 == plan.npass;
+        const uint32_t always = inverse && last_strided ? 1u : 0u;   // this pass's table carries N^-1
+        uint32_t tw_mode = 1, tw_shift = 0, prefetch = 0;
+        const Fr* table = nullptr;
+        if (log_ni <= 16) {
+            tw_mode = 0;
+            tw_shift = 16 - log_ni;
+            table = always ? mid_scaled : ctx->tw_mid[dir];
+        } else if (big && log_ni <= 24) {
+            tw_mode = 0;
+            tw_shift = 24 - log_ni;
+            table = big;
+            prefetch = 1;
+        }
         uint32_t threads = R * T / 8;
         if (threads > NTT_THREADS) threads = NTT_THREADS;
         if (threads < 32) threads = 32;
         KZG_LAUNCH(ctx, ntt_strided_pass_kernel, grid, threads, sizeof(Fr) * (R * T + R / 2), src, src_n, tmp, rb, T,
-                   log_stride, use_mid, scaled, ctx->tw_lo[dir], ctx->tw_hi[dir], scaled ? hi_scaled : ctx->tw_hi[dir],
-                   ctx->tw_mid[dir]);
+                   log_stride, tw_mode, tw_shift, always, prefetch, ctx->tw_lo[dir], ctx->tw_hi[dir], table);
         src = tmp;
         src_n = N;
     }

@@ -499,3 +499,26 @@ def test_ntt_tile_widths(curve, tile):
         assert from_mont(ev.eval.tobytes()) == opoly.ntt(coefs + [0] * (16384 - 3000))
     finally:
         curve.set_option("ntt_tile", -1)
+
+
+def test_ntt_direct_twiddle_table(curve):
+    """transforms of 2^17 .. 2^24 points take the first pass boundary's twiddles from the 512 MB direct table
+    (ntt_big_table = 1, default) or from the hi x lo composite (0): same bytes, forward and inverse; 2^17 also against
+    the oracle"""
+    from kzg_grandsums_study_b200 import synthetic
+    try:
+        for log_n in (17, 19, 22):
+            n = 1 << log_n
+            a = synthetic.random_fr_std(400 + log_n, n).tobytes()
+            buf = curve.to_device(a)
+            got = {}
+            for flag in (2, 0):                      # 2: the table from 2^17 points on (default 1: from 2^21)
+                curve.set_option("ntt_big_table", flag)
+                got[flag] = (curve.Fr.fft(buf).tobytes(), curve.Fr.ifft(buf).tobytes())
+            assert got[0] == got[1], log_n
+            assert curve.Fr.ifft(curve.Fr.fft(buf)).tobytes() == a
+            if log_n == 17:
+                vals = from_mont(a)
+                assert from_mont(got[2][0]) == opoly.ntt(vals)
+    finally:
+        curve.set_option("ntt_big_table", -1)
