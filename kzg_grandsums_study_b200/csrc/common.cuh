@@ -26,7 +26,7 @@ struct MsmTuning {
     uint32_t host_piece_min_log = 21;     // ... pieces from 2^this points on (2^21: the 8-GPU shard, 8.3 -> 7.5 ms e2e)
     int split_min_log = -1, split_max_log = -1;  // two-lane split of ONE msm (off: measured slower since the affine rounds)
     int merge = 1;                  // commitments of one round over one table as one merged pipeline
-    int ntt_big_table = 1;          // 512 MB direct twiddle table for the first pass boundary: 0 never, 1 from 2^21 points, 2 from 2^17
+    int ntt_big_table = 1;          // 512 MB direct twiddle table for the first pass boundary: 0 never, 1 from 2^19 points, 2 from 2^17
     int ntt_tile = 8;               // NTT tile width in elements (8: 256-byte rows, 256 threads; 4: 128-byte rows, 128 threads)
     int timeline = 0;               // debug: print where the time of every affine round goes (events on all three streams)
 };

@@ -146,14 +146,15 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
 //   tw_mode 0: table[e << tw_shift]: `mid` (w_{2^16}^e, 2 MB, L2-resident) for N_i <= 2^16 -- for an inverse transform the
 //              copy of `mid` scaled by N^-1 on the LAST strided pass, so that the scaling costs nothing --, `big`
 //              (w_{2^24}^e, 512 MB of HBM per direction, built on first use) for 2^17 <= N_i <= 2^24: one random 32-byte
-//              gather per element, whose sectors the block asks the L2 for (prefetch.global.L2) before it starts its
-//              butterflies -- the pass is bound by the integer pipe, the memory system has the room;
+//              gather per element (ld.global.nc.L2::64B: 64 bytes of DRAM traffic each) -- the pass is bound by the
+//              integer pipe, the memory system has the room (an L2 prefetch of the tile's twiddles before the butterflies
+//              was measured: 128-byte lines fetched, partly twice, and 3.59 instead of 3.53 ms);
 //   tw_mode 1: the hi x lo composite (two products), transforms above 2^24 only.
 // `always`: the table carries a scale factor, so e = 0 is not a shortcut.
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_strided_pass_kernel(const Fr* __restrict__ src, uint64_t n_in,
                                                                        Fr* __restrict__ dst, uint32_t rbits, uint32_t T,
                                                                        uint32_t log_stride, uint32_t tw_mode, uint32_t tw_shift,
-                                                                       uint32_t always, uint32_t prefetch,
+                                                                       uint32_t always, uint32_t big_table,
                                                                        const Fr* __restrict__ tw_lo,
                                                                        const Fr* __restrict__ tw_hi,
                                                                        const Fr* __restrict__ tw_table) {
@@ -190,13 +191,6 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_strided_pass_kernel(const 
     }
     smem_twiddles(tw, rbits, tw_hi);
     const uint32_t log_ni = rbits + log_stride;
-    if (prefetch) {  // the boundary twiddles of this tile: 2048 scattered sectors of the big table, wanted ~50 us from now
-        for (uint32_t idx = threadIdx.x; idx < R * T; idx += blockDim.x) {
-            const uint32_t c = idx % T, k = bitrev(idx / T, rbits);
-            const uint64_t e = ((uint64_t)k * (c0 + c)) & ((1ull << log_ni) - 1);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(tw_table + (e << tw_shift)));
-        }
-    }
     mbar_wait(&bar, 0);
     __syncthreads();
     smem_dif(sh, rbits, T, tw);
@@ -210,7 +204,20 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_strided_pass_kernel(const 
         uint64_t col = c0 + c;
         uint64_t e = ((uint64_t)k * col) & ((1ull << log_ni) - 1);
         if (always || e != 0) {
-            if (tw_mode == 0) v = fp_mul(v, fp_load<FrP>(tw_table + (e << tw_shift)));
+            if (tw_mode == 0) {
+                Fr w;
+                if (big_table) {  // the big table: one 32-byte record of a 512 MB array -- ask DRAM for 64 bytes, not the 128-byte line
+                    const uint4* q = reinterpret_cast<const uint4*>(tw_table + (e << tw_shift));
+                    uint4 a, b;
+                    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(q));
+                    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(q + 1));
+                    w.l[0] = a.x; w.l[1] = a.y; w.l[2] = a.z; w.l[3] = a.w;
+                    w.l[4] = b.x; w.l[5] = b.y; w.l[6] = b.z; w.l[7] = b.w;
+                } else {
+                    w = fp_load<FrP>(tw_table + (e << tw_shift));
+                }
+                v = fp_mul(v, w);
+            }
             else v = fp_mul(v, tw_lookup(tw_lo, tw_hi, (uint32_t)(e << shift)));
         }
         fp_store(dst + base + (uint64_t)k * S + c, v);
@@ -428,8 +435,8 @@ int ntt_run(kzg_ctx* ctx, const Fr* in, uint64_t n_in, Fr* out, uint32_t log_n, 
     const Fr* mid_scaled = nullptr;
     if (inverse) KZG_TRY(ntt_scaled_mid(ctx, log_n, &mid_scaled));  // (the last strided pass applies N^-1 with its twiddles)
     const Fr* big = nullptr;
-    // (measured: 3.58 vs 3.75 ms at 2^24, 0.434 vs 0.450 at 2^21, but 0.258 vs 0.250 at 2^20 -- sparse use of the table's lines)
-    if (log_n >= (ctx->tuning.ntt_big_table > 1 ? 17u : 21u) && log_n <= 24 && ctx->tuning.ntt_big_table)
+    // (measured: 3.53 vs 3.75 ms at 2^24, 0.428 vs 0.450 at 2^21, 0.240 vs 0.250 at 2^20, 0.146 vs 0.150 at 2^19, level at 2^18)
+    if (log_n >= (ctx->tuning.ntt_big_table > 1 ? 17u : 19u) && log_n <= 24 && ctx->tuning.ntt_big_table)
         KZG_TRY(ntt_big_table(ctx, dir, &big));
     Fr* tmp = nullptr;
     KZG_CUDA(ctx, cudaMallocAsync((void**)&tmp, sizeof(Fr) * N, ctx->stream));
@@ -447,7 +454,7 @@ int ntt_run(kzg_ctx* ctx, const Fr* in, uint64_t n_in, Fr* out, uint32_t log_n, 
         const uint32_t grid = (uint32_t)(N / ((uint64_t)R * T));
         const bool last_strided = i + 2 == plan.npass;
         const uint32_t always = inverse && last_strided ? 1u : 0u;   // this pass's table carries N^-1
-        uint32_t tw_mode = 1, tw_shift = 0, prefetch = 0;
+        uint32_t tw_mode = 1, tw_shift = 0, big_table = 0;
         const Fr* table = nullptr;
         if (log_ni <= 16) {
             tw_mode = 0;
@@ -457,13 +464,13 @@ int ntt_run(kzg_ctx* ctx, const Fr* in, uint64_t n_in, Fr* out, uint32_t log_n, 
             tw_mode = 0;
             tw_shift = 24 - log_ni;
             table = big;
-            prefetch = 1;
+            big_table = 1;
         }
         uint32_t threads = R * T / 8;
         if (threads > NTT_THREADS) threads = NTT_THREADS;
         if (threads < 32) threads = 32;
         KZG_LAUNCH(ctx, ntt_strided_pass_kernel, grid, threads, sizeof(Fr) * (R * T + R / 2), src, src_n, tmp, rb, T,
-                   log_stride, tw_mode, tw_shift, always, prefetch, ctx->tw_lo[dir], ctx->tw_hi[dir], table);
+                   log_stride, tw_mode, tw_shift, always, big_table, ctx->tw_lo[dir], ctx->tw_hi[dir], table);
         src = tmp;
         src_n = N;
     }

@@ -515,7 +515,7 @@ def test_ntt_direct_twiddle_table(curve):
             for flag in (2, 0):                      # 2: the table from 2^17 points on (default 1: from 2^21)
                 curve.set_option("ntt_big_table", flag)
                 got[flag] = (curve.Fr.fft(buf).tobytes(), curve.Fr.ifft(buf).tobytes())
-            assert got[0] == got[1], log_n
+            assert got[0] == got[2], log_n
             assert curve.Fr.ifft(curve.Fr.fft(buf)).tobytes() == a
             if log_n == 17:
                 vals = from_mont(a)
