@@ -329,7 +329,7 @@ int grand_terms(kzg_ctx* ctx, int kind, const Fr* ev_f, const Fr* ev_t, const Fr
 }
 
 // ------------------------------------------------------------------------------------------------
-// exclusive scan over Fr (add or mul monoid): reduce-then-scan in three launches.
+// exclusive scan over Fr (add or mul monoid): single pass, decoupled look-back (below).
 // Block tile = SC_THREADS * SC_E contiguous elements; thread t owns SC_E contiguous elements.
 // ------------------------------------------------------------------------------------------------
 constexpr int SC_THREADS = 256;
@@ -367,68 +367,102 @@ template <int KIND> __device__ __forceinline__ Fr block_inclusive_scan(Fr v, Fr*
     return scan_op<KIND>(carry, v);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(const Fr* __restrict__ in, uint64_t n, Fr* __restrict__ agg) {
-    __shared__ Fr sh[SC_THREADS / 32];
-    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_E;
-    Fr acc = scan_identity<KIND>();
-#pragma unroll
-    for (int k = 0; k < SC_E; k++) {
-        uint64_t i = base + k;
-        if (i < n) acc = scan_op<KIND>(acc, fp_load<FrP>(in + i));
-    }
-    Fr tot;
-    block_inclusive_scan<KIND>(acc, sh, tot);
-    if (threadIdx.x == 0) fp_store(agg + blockIdx.x, tot);
+// Single-pass scan with DECOUPLED LOOK-BACK (Merrill & Garland): every tile is read once and written once (64 N bytes),
+// in one launch.  A block takes its tile from an atomic ticket (so it only ever waits for tiles whose blocks are already
+// running), reduces it, publishes the tile AGGREGATE (flag 1), then its first warp looks back over the predecessors --
+// 32 tiles per step, each lane one tile: an INCLUSIVE prefix (flag 2) ends the walk, aggregates are folded in -- and
+// publishes its own inclusive prefix (flag 2).  Both monoids (Fr addition for the grand sum, Fr multiplication for the
+// grand product) are commutative, so the lanes' values are combined by a plain shuffle tree.  Values are 32 bytes, flags
+// separate words: value stores, __threadfence(), flag store on the writer; flag load (volatile), __threadfence(), value
+// loads that bypass L1 on the reader.
+struct ScanLookback {
+    uint32_t* flags;     // per tile: 0 nothing yet, 1 aggregate published, 2 inclusive prefix published
+    Fr* aggregate;       // per tile
+    Fr* inclusive;       // per tile; inclusive[ntiles - 1] is the grand total
+    uint32_t* ticket;
+};
+__device__ __forceinline__ Fr ld_cg_fr(const Fr* p) {
+    Fr r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 a = __ldcg(q), b = __ldcg(q + 1);
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
 }
-
-// single block: exclusive scan of the block aggregates in place; total -> agg[nblk]
 template <int KIND>
-__global__ void __launch_bounds__(SC_THREADS) scan_aggregates_kernel(Fr* __restrict__ agg, uint32_t nblk) {
+__global__ void __launch_bounds__(SC_THREADS) scan_lookback_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, uint64_t n,
+                                                                   ScanLookback st) {
     __shared__ Fr sh[SC_THREADS / 32];
-    const uint32_t per = (nblk + SC_THREADS - 1) / SC_THREADS;
-    const uint32_t lo = min(threadIdx.x * per, nblk), hi = min(lo + per, nblk);
-    Fr acc = scan_identity<KIND>();
-    for (uint32_t k = lo; k < hi; k++) acc = scan_op<KIND>(acc, fp_load<FrP>(agg + k));
-    Fr tot;
-    Fr incl = block_inclusive_scan<KIND>(acc, sh, tot);
-    // exclusive prefix for this thread's run = incl "minus" acc: recompute by carrying forward instead
-    // (mul monoid has no cheap inverse): shift through shared memory
     __shared__ Fr sh_incl[SC_THREADS];
-    fp_store(sh_incl + threadIdx.x, incl);
+    __shared__ Fr sh_prefix;
+    __shared__ uint32_t sh_tile;
+    if (threadIdx.x == 0) sh_tile = atomicAdd(st.ticket, 1u);
     __syncthreads();
-    Fr run = threadIdx.x == 0 ? scan_identity<KIND>() : fp_load<FrP>(sh_incl + threadIdx.x - 1);
-    for (uint32_t k = lo; k < hi; k++) {
-        Fr x = fp_load<FrP>(agg + k);
-        fp_store(agg + k, run);
-        run = scan_op<KIND>(run, x);
-    }
-    if (threadIdx.x == 0) fp_store(agg + nblk, tot);
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(SC_THREADS) scan_apply_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, uint64_t n,
-                                                                const Fr* __restrict__ agg) {
-    __shared__ Fr sh[SC_THREADS / 32];
-    __shared__ Fr sh_incl[SC_THREADS];
-    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_E;
+    const uint32_t tile = sh_tile;
+    const uint64_t base = (uint64_t)tile * SC_TILE + (uint64_t)threadIdx.x * SC_E;
     Fr v[SC_E];
     Fr acc = scan_identity<KIND>();
 #pragma unroll
     for (int k = 0; k < SC_E; k++) {
-        uint64_t i = base + k;
+        const uint64_t i = base + k;
         v[k] = i < n ? fp_load<FrP>(in + i) : scan_identity<KIND>();
         acc = scan_op<KIND>(acc, v[k]);
     }
     Fr tot;
-    Fr incl = block_inclusive_scan<KIND>(acc, sh, tot);
+    const Fr incl = block_inclusive_scan<KIND>(acc, sh, tot);
     fp_store(sh_incl + threadIdx.x, incl);
+    if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        Fr prefix = scan_identity<KIND>();
+        if (tile == 0) {
+            if (lane == 0) {
+                fp_store(st.inclusive, tot);
+                __threadfence();
+                *(volatile uint32_t*)st.flags = 2u;
+            }
+        } else {
+            if (lane == 0) {
+                fp_store(st.aggregate + tile, tot);
+                __threadfence();
+                *(volatile uint32_t*)(st.flags + tile) = 1u;
+            }
+            int64_t window = (int64_t)tile - 1;  // lane l inspects tile `window - l`
+            while (true) {
+                const int64_t p = window - (int64_t)lane;
+                uint32_t flag = 2u;              // lanes before tile 0 behave like an (identity) inclusive prefix
+                if (p >= 0) {
+                    do {
+                        flag = *(volatile const uint32_t*)(st.flags + p);
+                    } while (flag == 0u);
+                }
+                __threadfence();
+                const uint32_t done_mask = __ballot_sync(0xffffffffu, flag == 2u);
+                const uint32_t stop = done_mask ? (uint32_t)__ffs(done_mask) - 1u : 32u;  // first lane with an inclusive prefix
+                Fr val = scan_identity<KIND>();
+                if (p >= 0 && lane <= stop) val = ld_cg_fr(flag == 2u ? st.inclusive + p : st.aggregate + p);
+#pragma unroll
+                for (uint32_t d = 16; d >= 1; d >>= 1) {
+                    const Fr o = shfl_down_fr(val, d);
+                    val = scan_op<KIND>(val, o);  // (lanes beyond `stop` hold the identity)
+                }
+                if (lane == 0) prefix = scan_op<KIND>(val, prefix);
+                if (done_mask) break;
+                window -= 32;
+            }
+            if (lane == 0) {
+                fp_store(st.inclusive + tile, scan_op<KIND>(prefix, tot));
+                __threadfence();
+                *(volatile uint32_t*)(st.flags + tile) = 2u;
+            }
+        }
+        if (lane == 0) fp_store(&sh_prefix, prefix);
+    }
     __syncthreads();
-    Fr run = fp_load<FrP>(agg + blockIdx.x);
+    Fr run = fp_load<FrP>(&sh_prefix);
     if (threadIdx.x > 0) run = scan_op<KIND>(run, fp_load<FrP>(sh_incl + threadIdx.x - 1));
 #pragma unroll
     for (int k = 0; k < SC_E; k++) {
-        uint64_t i = base + k;
+        const uint64_t i = base + k;
         if (i < n) fp_store(out + i, run);
         run = scan_op<KIND>(run, v[k]);
     }
@@ -437,24 +471,27 @@ __global__ void __launch_bounds__(SC_THREADS) scan_apply_kernel(const Fr* __rest
 int fr_exclusive_scan(kzg_ctx* ctx, const Fr* in, Fr* out, uint64_t n, ScanKind kind, Fr* total_host) {
     if (n == 0) return KZG_OK;
     const uint32_t nblk = grid_for(n, SC_TILE);
-    Fr* agg = nullptr;
-    KZG_CUDA(ctx, cudaMallocAsync((void**)&agg, sizeof(Fr) * (nblk + 1), ctx->stream));
-    if (kind == SCAN_ADD) {
-        KZG_LAUNCH(ctx, scan_reduce_kernel<SCAN_ADD>, nblk, SC_THREADS, 0, in, n, agg);
-        KZG_LAUNCH(ctx, scan_aggregates_kernel<SCAN_ADD>, 1, SC_THREADS, 0, agg, nblk);
-        KZG_LAUNCH(ctx, scan_apply_kernel<SCAN_ADD>, nblk, SC_THREADS, 0, in, out, n, agg);
-    } else {
-        KZG_LAUNCH(ctx, scan_reduce_kernel<SCAN_MUL>, nblk, SC_THREADS, 0, in, n, agg);
-        KZG_LAUNCH(ctx, scan_aggregates_kernel<SCAN_MUL>, 1, SC_THREADS, 0, agg, nblk);
-        KZG_LAUNCH(ctx, scan_apply_kernel<SCAN_MUL>, nblk, SC_THREADS, 0, in, out, n, agg);
-    }
+    // state: [flags: nblk + 1 words (the last one is the ticket)] [aggregates: nblk] [inclusive prefixes: nblk]
+    const size_t flag_bytes = ((size_t)(nblk + 1) * sizeof(uint32_t) + 31) / 32 * 32;
+    uint8_t* state = nullptr;
+    KZG_CUDA(ctx, cudaMallocAsync((void**)&state, flag_bytes + 2 * sizeof(Fr) * nblk, ctx->stream));
+    KZG_CUDA(ctx, cudaMemsetAsync(state, 0, flag_bytes, ctx->stream));
+    ScanLookback st;
+    st.flags = (uint32_t*)state;
+    st.ticket = st.flags + nblk;
+    st.aggregate = (Fr*)(state + flag_bytes);
+    st.inclusive = st.aggregate + nblk;
+    if (kind == SCAN_ADD)
+        KZG_LAUNCH(ctx, scan_lookback_kernel<SCAN_ADD>, nblk, SC_THREADS, 0, in, out, n, st);
+    else
+        KZG_LAUNCH(ctx, scan_lookback_kernel<SCAN_MUL>, nblk, SC_THREADS, 0, in, out, n, st);
     KZG_CHECK_LAUNCH(ctx);
     if (total_host) {
-        KZG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, agg + nblk, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        KZG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, st.inclusive + (nblk - 1), sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
         KZG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         memcpy(total_host, ctx->pinned, sizeof(Fr));
     }
-    KZG_CUDA(ctx, cudaFreeAsync(agg, ctx->stream));
+    KZG_CUDA(ctx, cudaFreeAsync(state, ctx->stream));
     return KZG_OK;
 }
 
