@@ -315,6 +315,27 @@ class Curve(HostCurve):
             hit = self._srs_cache[key] = (h, power.value, ident)
         return hit[0], hit[1]
 
+    def load_lagrange_srs(self, ptau_path, nBits):
+        """[L_i(tau)]_1, i < 2^nBits, derived on the device from the monomial points of a .ptau (kzg_srs_lagrange; a
+        one-off per (file, size), cached like load_srs).  `Evaluations.commit(lagrange)` / kzg_commit over it commits a
+        polynomial given by its evaluations on H -- same point as committing its iNTT over the monomial SRS."""
+        n = 1 << nBits
+        mono, _ = self.load_srs(ptau_path, n)
+        path = os.path.abspath(ptau_path)
+        st = os.stat(path)
+        key = (path, "lagrange", int(nBits))
+        ident = (st.st_mtime_ns, st.st_size)
+        hit = self._srs_cache.get(key)
+        if hit is not None and hit[2] != ident:
+            self.lib.kzg_srs_free(self.ctx, hit[0])
+            hit = None
+        if hit is None:
+            h = C.c_void_p()
+            self.check(self.lib.kzg_srs_lagrange(self.ctx, mono, nBits, C.byref(h)))
+            self.check(self.lib.kzg_srs_precompute(self.ctx, h, 0))
+            hit = self._srs_cache[key] = (h, nBits, ident)
+        return hit[0]
+
     def terminate(self):
         if self.ctx:
             for entry in self._srs_cache.values():

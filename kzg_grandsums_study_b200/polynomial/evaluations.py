@@ -24,6 +24,15 @@ class Evaluations:
         curve.check(curve.lib.kzg_fr_extend_ntt(curve.ctx, coef.handle, extension, C.byref(out)))
         return Evaluations(curve.wrap(out), curve)
 
+    def commit(self, lagrange_srs):
+        """[p(tau)]_1 of the polynomial these are the evaluations of (Montgomery form, on H), committed DIRECTLY over the
+        Lagrange-basis SRS of curve.load_lagrange_srs(...) -- the same 64 bytes as
+        Polynomial.fromEvaluations(...).multiExponentiation(monomial SRS), without the iNTT"""
+        d = self.curve.to_device(self.eval)
+        out = bytearray(64)
+        self.curve.check(self.curve.lib.kzg_commit(self.curve.ctx, lagrange_srs, d.handle, as_ptr(out)))
+        return bytes(out)
+
     @staticmethod
     def fromArray(array, curve):                                # evaluations.js:23-29
         return Evaluations(b"".join(bytes(a) for a in array), curve)

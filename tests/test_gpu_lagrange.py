@@ -84,3 +84,17 @@ def test_lagrange_needs_enough_points(curve, tau):
             curve.check(curve.lib.kzg_srs_lagrange(curve.ctx, srs, 3, C.byref(lag)))
     finally:
         curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+def test_host_layer_commit_from_evaluations(curve, ptau_factory):
+    """Evaluations.commit(curve.load_lagrange_srs(ptau, nBits)) == Polynomial.fromEvaluations(...).multiExponentiation(srs):
+    the [F], [T] of a proof from their evaluations, no iNTT"""
+    from kzg_grandsums_study_b200.polynomial import Evaluations, Polynomial
+    nbits = 10
+    path = ptau_factory(nbits)
+    f = inputs.random_column(321, 1 << nbits)
+    ev = Evaluations(bn.fr_vec_to_mont_bytes(f), curve)
+    lag = curve.load_lagrange_srs(path, nbits)
+    srs = curve.load_srs(path, 2 << nbits)
+    assert ev.commit(lag) == Polynomial.fromEvaluations(ev.eval, curve).multiExponentiation(srs)
+    assert curve.load_lagrange_srs(path, nbits) is lag or curve.load_lagrange_srs(path, nbits).value == lag.value
