@@ -91,6 +91,15 @@ struct MsmJobs {
     uint32_t count;
 };
 
+// One piece of an MSM handing its folded bucket sums (one point per non-empty bucket, addressed through pbase) to the
+// reduction of a later piece over the same bucket geometry; `ready` is recorded on the producing stream after the fold.
+struct MsmReduceLink {
+    const G1XYZZ* partials = nullptr;
+    const uint32_t* pbase = nullptr;
+    uint32_t nkeys = 0;
+    cudaEvent_t ready = nullptr;
+};
+
 __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, uint32_t pos, uint32_t c) {
     // bits [pos, pos+c) of a 256-bit little-endian integer, zero beyond bit 255
     uint32_t word = pos >> 5, off = pos & 31;
@@ -1238,8 +1247,12 @@ __global__ void __launch_bounds__(512) msm_collapse_huge_kernel(G1XYZZ* __restri
 
 // level 0 reads the accumulate output through pbase: one point per bucket (msm_fold / msm_collapse have folded the
 // partial sums of a bucket into its first slot), none for an empty bucket
+// (in2 / pbase2: the bucket points of an earlier piece of the same MSM over the same bucket geometry -- a host-scalar MSM
+// is cut into pieces so that its uploads hide behind compute; the pieces share THIS reduction instead of paying one each)
 __global__ void __launch_bounds__(RED_THREADS, 4) msm_reduce_level0_kernel(const G1XYZZ* __restrict__ in,
                                                                            const uint32_t* __restrict__ pbase,
+                                                                           const G1XYZZ* __restrict__ in2,
+                                                                           const uint32_t* __restrict__ pbase2,
                                                                            uint32_t nbuckets, uint32_t radix,
                                                                            G1XYZZ* __restrict__ out_u, uint32_t n_out,
                                                                            G1XYZZ* __restrict__ out_t) {
@@ -1256,6 +1269,13 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_reduce_level0_kernel(const
         if (pbase[key + 1] != a) {
             G1XYZZ o = load_xyzz(in + a);
             xyzz_add_fn(run, o);
+        }
+        if (in2) {
+            const uint32_t a2 = pbase2[key];
+            if (pbase2[key + 1] != a2) {
+                G1XYZZ o = load_xyzz(in2 + a2);
+                xyzz_add_fn(run, o);
+            }
         }
         xyzz_add_fn(tot, run);
     }
@@ -1612,7 +1632,8 @@ cudaEvent_t order_event(kzg_ctx* ctx) {
 
 // `jobs.count` MSMs over the same bases as one pipeline; results[j] receives the XYZZ sum of job j (device memory).
 // More than one job needs the window-table flavour.
-int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XYZZ* results) {
+int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XYZZ* results, const MsmReduceLink* add_in,
+                  MsmReduceLink* defer_out) {
     const uint32_t njobs = jobs.count;
     if (njobs == 0) return KZG_OK;
     if (njobs > MSM_MAX_JOBS) return set_err(ctx, KZG_ERR_ARG, "msm: too many jobs in one pipeline");
@@ -1969,13 +1990,31 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
         const uint64_t max_multi = max_tasks < nkeys ? max_tasks : nkeys;
         KZG_LAUNCH(ctx, msm_fold_kernel, (uint32_t)((max_multi + 127) / 128), 128, 0, partials, segoff, multi + 1, multi);
     }
+    if (defer_out) {  // this piece's bucket sums go into a later piece's reduction
+        defer_out->partials = partials;
+        defer_out->pbase = segoff;
+        defer_out->nkeys = nkeys;
+        defer_out->ready = order_event(ctx);
+        KZG_CUDA(ctx, cudaEventRecord(defer_out->ready, ctx->stream));
+        timed_end(ctx, KZG_TIMED_MSM_REDUCE);
+        KZG_CHECK_LAUNCH(ctx);
+        return KZG_OK;
+    }
+    const G1XYZZ* in2 = nullptr;
+    const uint32_t* pbase2 = nullptr;
+    if (add_in) {
+        if (add_in->nkeys != nkeys) return set_err(ctx, KZG_ERR_ARG, "msm: linked pieces must share the bucket geometry");
+        KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, add_in->ready, 0));
+        in2 = add_in->partials;
+        pbase2 = add_in->pbase;
+    }
     // table flavour: every bucket set IS a result (one per job); raw flavour: the sets are the windows of one result
     G1XYZZ* sums_out = g.table ? results : set_sums;
     {
         const dim3 grid((tg.n1 + RED_THREADS - 1) / RED_THREADS, g.nsets);
         // (measured: calling the shared addition at 126 registers / 16 warps per SM beats the inlined 168-register
         // version with its spills: 0.60 vs 0.66 ms for the whole reduction at 2^19 buckets)
-        KZG_LAUNCH(ctx, msm_reduce_level0_kernel, grid, RED_THREADS, 0, partials, segoff, g.nbuckets, 1u << tg.k0, u_arrays, tg.n1,
+        KZG_LAUNCH(ctx, msm_reduce_level0_kernel, grid, RED_THREADS, 0, partials, segoff, in2, pbase2, g.nbuckets, 1u << tg.k0, u_arrays, tg.n1,
                    tvals);
     }
     {
@@ -2015,7 +2054,18 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     jobs.n[0] = n;
     jobs.montgomery = src.montgomery ? 1u : 0u;
     jobs.count = 1;
-    return msm_run_multi(ctx, bases, jobs, result_dev);
+    return msm_run_multi(ctx, bases, jobs, result_dev, nullptr, nullptr);
+}
+// one piece of a linked pair (see MsmReduceLink)
+static int msm_run_linked(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev,
+                          const MsmReduceLink* add_in, MsmReduceLink* defer_out) {
+    MsmJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    jobs.scalars[0] = src.scalars;
+    jobs.n[0] = n;
+    jobs.montgomery = src.montgomery ? 1u : 0u;
+    jobs.count = 1;
+    return msm_run_multi(ctx, bases, jobs, result_dev, add_in, defer_out);
 }
 
 int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t count, uint8_t out[64]) {
@@ -2133,7 +2183,7 @@ int msm_run_batch(kzg_ctx* ctx, const MsmJob* jobs, uint32_t count, uint8_t* out
             mj.n[j] = jobs[gr.first + j].n;
             if (jobs[gr.first + j].src.montgomery) mj.montgomery |= 1u << j;
         }
-        r = msm_run_multi(ctx, jobs[gr.first].bases, mj, xyzz_slots + gr.first);
+        r = msm_run_multi(ctx, jobs[gr.first].bases, mj, xyzz_slots + gr.first, nullptr, nullptr);
         if (r == KZG_OK) {
             KZG_LAUNCH(ctx, g1_finish_many_kernel, gr.count, 32, 0, xyzz_slots + gr.first, affine_slots + gr.first);
             if (cudaGetLastError() != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, "g1_finish launch failed");
@@ -2329,9 +2379,14 @@ static int srs_msm_host_pieces(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const
     if (n >= (1ull << ctx->tuning.host_piece_min_log)) {
         // every piece pays the fixed part of an MSM again (~1.3 ms with 2^19 buckets, ~2.2 ms with the 2^21 buckets of a
         // c = 22 table): three pieces of 1/8, 2/8, 5/8 for the former, two of 3/16, 13/16 for the latter
+        // Two pieces (3/16, 13/16) over a window table: they SHARE one bucket reduction (the first piece hands its folded
+        // bucket sums to the second one's level 0, MsmReduceLink), so a piece costs its sort and accumulation only.
+        // Without a table (per-window bucket sets whose geometry depends on the piece size) every piece reduces on its
+        // own: three pieces of 1/8, 2/8, 5/8.
+        const bool table_flavour = srs->table && ctx->msm_window == 0;
         uint64_t cut[4] = {0, n / 8, n / 8 + n / 4, n};
         parts = 3;
-        if (n < (1ull << 22) || (srs->table && srs->tab_c > 20 && ctx->msm_window == 0)) {
+        if (table_flavour) {
             parts = 2;
             cut[1] = n / 16 * 3;
             cut[2] = n;
@@ -2358,13 +2413,26 @@ static int srs_msm_host_pieces(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const
         }
         if (e != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, std::string("msm upload: ") + cudaGetErrorString(e));
         const bool lanes = ctx->lane == 0 && !ctx->no_split;
+        // (measured, e2e ms with / without: 6.05 / 6.57 at 2^21 points, 11.03 / 12.37 at 2^22, 20.71 / 21.06 at 2^23, but
+        // 37.76 / 37.50 at 2^24 -- there the second piece cannot start before its 416 MiB upload ends, the first piece's own
+        // reduction hides under that wait, and the shared one pays a third addition per bucket: host_link = 1 links below
+        // 2^24 points, 2 always, 0 never)
+        const bool link_wanted = ctx->tuning.host_link == 2 || (ctx->tuning.host_link == 1 && n < (1ull << 24));
+        const bool link = parts == 2 && lanes && table_flavour && link_wanted && cut[1] > 0 && cut[1] < n;
+        MsmReduceLink lk;
         for (uint32_t k = 0; k < parts && r == KZG_OK; k++) {
             const int lane = lanes ? (int)(k & 1) : 0;
             ctx->lane = lane;
             ctx->stream = lane ? ctx->aux_stream : main_stream;
             cudaStreamWaitEvent(ctx->stream, up[k], 0);
-            r = msm_run(ctx, srs_bases(ctx, srs, first + cut[k]), MsmScalarSrc{tmp + cut[k], false}, cut[k + 1] - cut[k], slots + k);
+            const MsmBases pb = srs_bases(ctx, srs, first + cut[k]);
+            const MsmScalarSrc ps{tmp + cut[k], false};
+            if (link)  // piece 0 (lane 0's arena) stops after its fold, piece 1 (lane 1's arena) reduces both
+                r = msm_run_linked(ctx, pb, ps, cut[k + 1] - cut[k], slots, k == 0 ? nullptr : &lk, k == 0 ? &lk : nullptr);
+            else
+                r = msm_run(ctx, pb, ps, cut[k + 1] - cut[k], slots + k);
         }
+        if (link) parts = 1;
         ctx->lane = 0;
         ctx->stream = main_stream;
         // (also on the error path: tmp is freed on the main stream, after every upload and every piece that was queued)

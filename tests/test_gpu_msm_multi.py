@@ -223,3 +223,35 @@ def test_two_contexts_on_two_devices(tau):
     finally:
         a.terminate()
         b.terminate()
+
+
+@pytest.mark.parametrize("log_n,table_c", [(21, 0), (22, 0), (21, 14)])
+def test_host_scalar_pieces_share_one_reduction(curve, tau, log_n, table_c):
+    """kzg_srs_msm_host cuts the scalars into two pieces whose uploads hide behind compute; with a window table the first
+    piece hands its folded bucket sums to the second piece's reduction (host_link = 1, default) instead of reducing on its
+    own (0).  Same point either way, equal to the resident-scalar MSM -- also with skewed scalars whose buckets are empty
+    in one piece and full in the other."""
+    import torch
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200._lib import as_ptr
+    lib, ctx = curve.lib, curve.ctx
+    n = 1 << log_n
+    srs = _srs(curve, tau, n, table_c)
+    try:
+        scal = synthetic.random_fr_std(1234 + log_n, n)
+        skew = scal.copy()
+        skew[: n // 4] = 0                      # the whole first piece contributes nothing
+        skew[n // 2:, 1:] = 0                   # 64-bit scalars: the upper windows are empty in the second piece
+        for data in (scal, skew):
+            host = torch.from_numpy(data.view(np.uint8).reshape(-1).copy()).pin_memory()
+            dev = curve.to_device(data.tobytes())
+            want = bytearray(64)
+            curve.check(lib.kzg_srs_msm(ctx, srs, 0, dev.handle, n, as_ptr(want)))
+            for link in (1, 2, 0):              # by size (links at these sizes) / always / never
+                curve.set_option("host_link", link)
+                got = bytearray(64)
+                curve.check(lib.kzg_srs_msm_host(ctx, srs, 0, as_ptr(host), n, as_ptr(got)))
+                assert bytes(got) == bytes(want), (log_n, table_c, link)
+    finally:
+        curve.set_option("host_link", -1)
+        curve.lib.kzg_srs_free(curve.ctx, srs)
