@@ -176,6 +176,30 @@ template <class P> __device__ bool selftest_field(uint64_t& s) {
     bool ok = true;
     ok &= fp_eq(fp_mul(a, b), fp_mul_portable(a, b));
     ok &= fp_eq(fp_mul(a, a), fp_mul_portable(a, a));
+    ok &= fp_eq(fp_sqr(a), fp_mul_portable(a, a));  // the dedicated squaring (100 wide MACs)
+    ok &= fp_eq(fp_sqr(fp_sub(b, c)), fp_mul_portable(fp_sub(b, c), fp_sub(b, c)));
+    {   // two products under one reduction, incl. the operands that maximise every intermediate total
+        const Fp<P> d = fp_sub(a, c), m1 = fp_neg(fp_one<P>());
+        ok &= fp_eq(fp_mul2(a, b, c, d), fp_add(fp_mul_portable(a, b), fp_mul_portable(c, d)));
+        ok &= fp_eq(fp_mul2_sub(a, b, c, d), fp_sub(fp_mul_portable(a, b), fp_mul_portable(c, d)));
+        ok &= fp_eq(fp_mul2(m1, m1, m1, m1), fp_dbl(fp_mul_portable(m1, m1)));
+        ok &= fp_eq(fp_mul2_sub(a, b, fp_zero<P>(), d), fp_mul_portable(a, b));
+        ok &= fp_is_zero(fp_mul2_sub(a, b, a, b));
+    }
+    {   // operands made of extreme limbs: every carry of the squaring's chains
+        Fp<P> e = a;
+        const uint64_t z = splitmix(s);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t pick = (uint32_t)(z >> (4 * i)) & 7u;
+            if (pick == 0) e.l[i] = 0xffffffffu;
+            else if (pick == 1) e.l[i] = 0;
+            else if (pick == 2) e.l[i] = 0x80000000u;
+            else if (pick == 3) e.l[i] = 1;
+        }
+        e.l[7] &= 0x1fffffffu;
+        ok &= fp_eq(fp_sqr(e), fp_mul_portable(e, e));
+    }
     ok &= fp_eq(fp_mul(fp_add(a, b), c), fp_add(fp_mul(a, c), fp_mul(b, c)));
     ok &= fp_eq(fp_sub(fp_add(a, b), b), a);
     ok &= fp_eq(fp_from_mont(fp_to_mont(a)), a);
@@ -190,6 +214,8 @@ __global__ void selftest_kernel(uint32_t n, unsigned int* fail) {
     Fq m1 = fp_neg(fp_one<FqP>());
     ok &= fp_eq(fp_mul(m1, m1), fp_one<FqP>());
     ok &= fp_eq(fp_mul(m1, m1), fp_mul_portable(m1, m1));
+    ok &= fp_eq(fp_sqr(m1), fp_one<FqP>()) && fp_is_zero(fp_sqr(fp_zero<FqP>())) && fp_eq(fp_sqr(fp_one<FqP>()), fp_one<FqP>());
+    ok &= fp_eq(fp_sqr(fp_neg(fp_one<FrP>())), fp_one<FrP>()) && fp_eq(fp_sqr(fp_one<FrP>()), fp_one<FrP>());
     ok &= fp_is_zero(fp_mul(fp_zero<FqP>(), m1));
     if ((i & 63) == 0) {
         Fq a = random_fp<FqP>(s);

@@ -106,7 +106,7 @@ KZG_HD void xyzz_madd(G1XYZZ& acc, const G1Affine& p) {
     Fq ppp = fp_mul(pp_, pp);
     Fq q = fp_mul(acc.x, pp);
     Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(q));
-    Fq y3 = fp_sub(fp_mul(r, fp_sub(q, x3)), fp_mul(acc.y, ppp));
+    Fq y3 = fp_mul2_sub(r, fp_sub(q, x3), acc.y, ppp);  // R (Q - X3) - Y1 PPP under one reduction
     acc.x = x3;
     acc.y = y3;
     acc.zz = fp_mul(acc.zz, pp);
@@ -138,7 +138,7 @@ KZG_HD void xyzz_add(G1XYZZ& acc, const G1XYZZ& b) {
     Fq ppp = fp_mul(pp_, pp);
     Fq q = fp_mul(u1, pp);
     Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(q));
-    Fq y3 = fp_sub(fp_mul(r, fp_sub(q, x3)), fp_mul(s1, ppp));
+    Fq y3 = fp_mul2_sub(r, fp_sub(q, x3), s1, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = fp_mul(fp_mul(acc.zz, b.zz), pp);

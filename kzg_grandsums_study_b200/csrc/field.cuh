@@ -416,8 +416,458 @@ template <class P> KZG_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #endif
 }
 
+// a b + c d with ONE interleaved reduction: the rows of fp_mul with a second product row before each reduction row --
+// 192 wide MACs instead of 256.  Every intermediate total stays below 3p + 3p 2^32 < 2^288 (the nine words of the
+// accumulator pair) and the result below (2 p^2 + p 2^256) / 2^256 < 1.38 p: one conditional subtraction.  The helper
+// sequence is emulated word by word, with every dropped carry asserted zero, in tools/gen_fp_sqr.py (check2).
+template <class P> KZG_HD Fp<P> fp_mul2(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+#if defined(__CUDA_ARCH__) && KZG_FAST_MUL
+    uint32_t x[8], y[8];
+    asm("mul.lo.u32 %0, %8, %12;\n\t mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t mul.hi.u32 %7, %11, %12;\n\t"
+        : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+        : "r"(a.l[0]), "r"(a.l[2]), "r"(a.l[4]), "r"(a.l[6]), "r"(b.l[0]));
+    asm("mul.lo.u32 %0, %8, %12;\n\t mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t mul.hi.u32 %7, %11, %12;\n\t"
+        : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7])
+        : "r"(a.l[1]), "r"(a.l[3]), "r"(a.l[5]), "r"(a.l[7]), "r"(b.l[0]));
+    cmad4(y, c.l[1], c.l[3], c.l[5], c.l[7], d.l[0]);
+    cmad4_top(x, c.l[0], c.l[2], c.l[4], c.l[6], d.l[0], y[7]);
+    {
+        uint32_t m = x[0] * P::INV;
+        cmad4(y, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+        cmad4_top(x, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m, y[7]);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        uint32_t* lo = (i & 1) ? y : x;
+        uint32_t* hi = (i & 1) ? x : y;
+        shift_mad4(lo[0], hi[1], hi, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+        cmad4_top(lo, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i], hi[7]);
+        cmad4(hi, c.l[1], c.l[3], c.l[5], c.l[7], d.l[i]);
+        cmad4_top(lo, c.l[0], c.l[2], c.l[4], c.l[6], d.l[i], hi[7]);
+        uint32_t m = lo[0] * P::INV;
+        cmad4(hi, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+        cmad4_top(lo, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m, hi[7]);
+    }
+    uint32_t t[8];
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, 0;\n\t"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]),
+          "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]));
+    return fp_final_sub<P>(t);
+#else
+    return fp_add(fp_mul(a, b), fp_mul(c, d));
+#endif
+}
+// a b - c d
+template <class P> KZG_HD Fp<P> fp_mul2_sub(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+    return fp_mul2(a, b, fp_neg(c), d);
+}
+
+// Dedicated squaring: 100 wide MACs instead of 128 (28 off-diagonal products doubled + 8 squares, then a Montgomery
+// reduction of the 512-bit result with the same even/odd rows as fp_mul).  The instruction list is produced AND emulated
+// word by word on the CPU by tools/gen_fp_sqr.py (carry bookkeeping checked there against a^2 / R mod p); kzg_selftest()
+// compares the compiled code with fp_mul_portable on the device.  Same canonical result as fp_mul(a, a).
+#ifndef KZG_FAST_SQR
+#define KZG_FAST_SQR 1
+#endif
 template <class P> KZG_HD Fp<P> fp_sqr(const Fp<P>& a) {
+#if defined(__CUDA_ARCH__) && KZG_FAST_MUL && KZG_FAST_SQR
+    // ---- GENERATED by tools/gen_fp_sqr.py (do not edit by hand) ----
+    const uint32_t a0 = a.l[0], a1 = a.l[1], a2 = a.l[2], a3 = a.l[3], a4 = a.l[4], a5 = a.l[5], a6 = a.l[6], a7 = a.l[7];
+    uint32_t e2, e3, e4, e5, e6, e7, o0, o1, o2, o3, o4, o5, o6, o7, e8, e9, o8, e10, o9, e11, o10, e12, o11, e13,
+        o12, o13, d15, d14, d13, d12, d11, d10, d9, d8, d7, d6, d5, d4, d3, d2, d1, T0, T1, T2, T3, T4, T5, T6, T7,
+        T8, T9, T10, T11, T12, T13, T14, T15, x0, x1, x2, x3, x4, x5, x6, x7, m, y0, y1, y2, y3, y4, y5, y6, y7, w,
+        t0, t1, t2, t3, t4, t5, t6, t7;
+    asm("mul.lo.u32 %0, %6, %7;\n\t"
+        "mul.hi.u32 %1, %6, %7;\n\t"
+        "mul.lo.u32 %2, %8, %7;\n\t"
+        "mul.hi.u32 %3, %8, %7;\n\t"
+        "mul.lo.u32 %4, %9, %7;\n\t"
+        "mul.hi.u32 %5, %9, %7;"
+        : "=r"(e2), "=r"(e3), "=r"(e4), "=r"(e5), "=r"(e6), "=r"(e7)
+        : "r"(a2), "r"(a0), "r"(a4), "r"(a6));
+    asm("mul.lo.u32 %0, %8, %9;\n\t"
+        "mul.hi.u32 %1, %8, %9;\n\t"
+        "mul.lo.u32 %2, %10, %9;\n\t"
+        "mul.hi.u32 %3, %10, %9;\n\t"
+        "mul.lo.u32 %4, %11, %9;\n\t"
+        "mul.hi.u32 %5, %11, %9;\n\t"
+        "mul.lo.u32 %6, %12, %9;\n\t"
+        "mul.hi.u32 %7, %12, %9;"
+        : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3), "=r"(o4), "=r"(o5), "=r"(o6), "=r"(o7)
+        : "r"(a1), "r"(a0), "r"(a3), "r"(a5), "r"(a7));
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %7, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %7, 0;\n\t"
+        "madc.hi.u32 %5, %9, %7, 0;"
+        : "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "=r"(e8), "=r"(e9)
+        : "r"(a3), "r"(a1), "r"(a5), "r"(a7));
+    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %8, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %8, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %8, %5;\n\t"
+        "addc.u32 %6, 0, 0;"
+        : "+r"(o2), "+r"(o3), "+r"(o4), "+r"(o5), "+r"(o6), "+r"(o7), "=r"(o8)
+        : "r"(a2), "r"(a1), "r"(a4), "r"(a6));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %6, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %6, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(e6), "+r"(e7), "+r"(e8), "+r"(e9), "=r"(e10)
+        : "r"(a4), "r"(a2), "r"(a6));
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %7, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %7, %4;\n\t"
+        "madc.hi.u32 %5, %9, %7, 0;"
+        : "+r"(o4), "+r"(o5), "+r"(o6), "+r"(o7), "+r"(o8), "=r"(o9)
+        : "r"(a3), "r"(a2), "r"(a5), "r"(a7));
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %5, %2;\n\t"
+        "madc.hi.u32 %3, %6, %5, 0;"
+        : "+r"(e8), "+r"(e9), "+r"(e10), "=r"(e11)
+        : "r"(a5), "r"(a3), "r"(a7));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %6, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %6, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(o6), "+r"(o7), "+r"(o8), "+r"(o9), "=r"(o10)
+        : "r"(a4), "r"(a3), "r"(a6));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, 0, 0;"
+        : "+r"(e10), "+r"(e11), "=r"(e12)
+        : "r"(a6), "r"(a4));
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %5, %2;\n\t"
+        "madc.hi.u32 %3, %6, %5, 0;"
+        : "+r"(o8), "+r"(o9), "+r"(o10), "=r"(o11)
+        : "r"(a5), "r"(a4), "r"(a7));
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, 0;"
+        : "+r"(e12), "=r"(e13)
+        : "r"(a7), "r"(a5));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, 0, 0;"
+        : "+r"(o10), "+r"(o11), "=r"(o12)
+        : "r"(a6), "r"(a5));
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, 0;"
+        : "+r"(o12), "=r"(o13)
+        : "r"(a7), "r"(a6));
+    asm("add.cc.u32 %0, %0, %13;\n\t"
+        "addc.cc.u32 %1, %1, %14;\n\t"
+        "addc.cc.u32 %2, %2, %15;\n\t"
+        "addc.cc.u32 %3, %3, %16;\n\t"
+        "addc.cc.u32 %4, %4, %17;\n\t"
+        "addc.cc.u32 %5, %5, %18;\n\t"
+        "addc.cc.u32 %6, %6, %19;\n\t"
+        "addc.cc.u32 %7, %7, %20;\n\t"
+        "addc.cc.u32 %8, %8, %21;\n\t"
+        "addc.cc.u32 %9, %9, %22;\n\t"
+        "addc.cc.u32 %10, %10, %23;\n\t"
+        "addc.cc.u32 %11, %11, %24;\n\t"
+        "addc.u32 %12, %12, 0;"
+        : "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "+r"(e8), "+r"(e9), "+r"(e10), "+r"(e11), "+r"(e12), "+r"(e13), "+r"(o13)
+        : "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6), "r"(o7), "r"(o8), "r"(o9), "r"(o10), "r"(o11), "r"(o12));
+    asm("shr.u32 %0, %15, 31;\n\t"
+        "shf.l.wrap.b32 %1, %16, %15, 1;\n\t"
+        "shf.l.wrap.b32 %2, %17, %16, 1;\n\t"
+        "shf.l.wrap.b32 %3, %18, %17, 1;\n\t"
+        "shf.l.wrap.b32 %4, %19, %18, 1;\n\t"
+        "shf.l.wrap.b32 %5, %20, %19, 1;\n\t"
+        "shf.l.wrap.b32 %6, %21, %20, 1;\n\t"
+        "shf.l.wrap.b32 %7, %22, %21, 1;\n\t"
+        "shf.l.wrap.b32 %8, %23, %22, 1;\n\t"
+        "shf.l.wrap.b32 %9, %24, %23, 1;\n\t"
+        "shf.l.wrap.b32 %10, %25, %24, 1;\n\t"
+        "shf.l.wrap.b32 %11, %26, %25, 1;\n\t"
+        "shf.l.wrap.b32 %12, %27, %26, 1;\n\t"
+        "shf.l.wrap.b32 %13, %28, %27, 1;\n\t"
+        "shl.b32 %14, %28, 1;"
+        : "=r"(d15), "=r"(d14), "=r"(d13), "=r"(d12), "=r"(d11), "=r"(d10), "=r"(d9), "=r"(d8), "=r"(d7), "=r"(d6), "=r"(d5), "=r"(d4), "=r"(d3), "=r"(d2), "=r"(d1)
+        : "r"(o13), "r"(e13), "r"(e12), "r"(e11), "r"(e10), "r"(e9), "r"(e8), "r"(e7), "r"(e6), "r"(e5), "r"(e4), "r"(e3), "r"(e2), "r"(o0));
+    asm("mul.lo.u32 %0, %16, %16;\n\t"
+        "mad.hi.cc.u32 %1, %16, %16, %17;\n\t"
+        "madc.lo.cc.u32 %2, %18, %18, %19;\n\t"
+        "madc.hi.cc.u32 %3, %18, %18, %20;\n\t"
+        "madc.lo.cc.u32 %4, %21, %21, %22;\n\t"
+        "madc.hi.cc.u32 %5, %21, %21, %23;\n\t"
+        "madc.lo.cc.u32 %6, %24, %24, %25;\n\t"
+        "madc.hi.cc.u32 %7, %24, %24, %26;\n\t"
+        "madc.lo.cc.u32 %8, %27, %27, %28;\n\t"
+        "madc.hi.cc.u32 %9, %27, %27, %29;\n\t"
+        "madc.lo.cc.u32 %10, %30, %30, %31;\n\t"
+        "madc.hi.cc.u32 %11, %30, %30, %32;\n\t"
+        "madc.lo.cc.u32 %12, %33, %33, %34;\n\t"
+        "madc.hi.cc.u32 %13, %33, %33, %35;\n\t"
+        "madc.lo.cc.u32 %14, %36, %36, %37;\n\t"
+        "madc.hi.u32 %15, %36, %36, %38;"
+        : "=r"(T0), "=r"(T1), "=r"(T2), "=r"(T3), "=r"(T4), "=r"(T5), "=r"(T6), "=r"(T7), "=r"(T8), "=r"(T9), "=r"(T10), "=r"(T11), "=r"(T12), "=r"(T13), "=r"(T14), "=r"(T15)
+        : "r"(a0), "r"(d1), "r"(a1), "r"(d2), "r"(d3), "r"(a2), "r"(d4), "r"(d5), "r"(a3), "r"(d6), "r"(d7), "r"(a4), "r"(d8), "r"(d9), "r"(a5), "r"(d10), "r"(d11), "r"(a6), "r"(d12), "r"(d13), "r"(a7), "r"(d14), "r"(d15));
+    asm("mov.b32 %0, %9;\n\t"
+        "mov.b32 %1, %10;\n\t"
+        "mov.b32 %2, %11;\n\t"
+        "mov.b32 %3, %12;\n\t"
+        "mov.b32 %4, %13;\n\t"
+        "mov.b32 %5, %14;\n\t"
+        "mov.b32 %6, %15;\n\t"
+        "mov.b32 %7, %16;\n\t"
+        "mul.lo.u32 %8, %0, %17;"
+        : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4), "=r"(x5), "=r"(x6), "=r"(x7), "=r"(m)
+        : "r"(T0), "r"(T1), "r"(T2), "r"(T3), "r"(T4), "r"(T5), "r"(T6), "r"(T7), "r"(P::INV));
+    asm("mul.lo.u32 %0, %8, %9;\n\t"
+        "mul.hi.u32 %1, %8, %9;\n\t"
+        "mul.lo.u32 %2, %10, %9;\n\t"
+        "mul.hi.u32 %3, %10, %9;\n\t"
+        "mul.lo.u32 %4, %11, %9;\n\t"
+        "mul.hi.u32 %5, %11, %9;\n\t"
+        "mul.lo.u32 %6, %12, %9;\n\t"
+        "mul.hi.u32 %7, %12, %9;"
+        : "=r"(y0), "=r"(y1), "=r"(y2), "=r"(y3), "=r"(y4), "=r"(y5), "=r"(y6), "=r"(y7)
+        : "r"(P::mod(1)), "r"(m), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7), "+r"(y7)
+        : "r"(P::mod(0)), "r"(m), "r"(P::mod(2)), "r"(P::mod(4)), "r"(P::mod(6)));
+    asm("add.u32 %0, %2, %3;\n\t"
+        "mul.lo.u32 %1, %0, %4;"
+        : "=r"(w), "=r"(m)
+        : "r"(y0), "r"(x1), "r"(P::INV));
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %10, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %10, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %10, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %10, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %10, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %10, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %10, 0;\n\t"
+        "madc.hi.u32 %8, %13, %10, 0;"
+        : "+r"(y0), "=r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7)
+        : "r"(P::mod(1)), "r"(m), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(y0), "+r"(y1), "+r"(y2), "+r"(y3), "+r"(y4), "+r"(y5), "+r"(y6), "+r"(y7), "+r"(x7)
+        : "r"(P::mod(0)), "r"(m), "r"(P::mod(2)), "r"(P::mod(4)), "r"(P::mod(6)));
+    asm("add.u32 %0, %2, %3;\n\t"
+        "mul.lo.u32 %1, %0, %4;"
+        : "=r"(w), "=r"(m)
+        : "r"(x0), "r"(y1), "r"(P::INV));
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %10, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %10, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %10, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %10, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %10, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %10, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %10, 0;\n\t"
+        "madc.hi.u32 %8, %13, %10, 0;"
+        : "+r"(x0), "=r"(y0), "+r"(y1), "+r"(y2), "+r"(y3), "+r"(y4), "+r"(y5), "+r"(y6), "+r"(y7)
+        : "r"(P::mod(1)), "r"(m), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7), "+r"(y7)
+        : "r"(P::mod(0)), "r"(m), "r"(P::mod(2)), "r"(P::mod(4)), "r"(P::mod(6)));
+    asm("add.u32 %0, %2, %3;\n\t"
+        "mul.lo.u32 %1, %0, %4;"
+        : "=r"(w), "=r"(m)
+        : "r"(y0), "r"(x1), "r"(P::INV));
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %10, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %10, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %10, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %10, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %10, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %10, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %10, 0;\n\t"
+        "madc.hi.u32 %8, %13, %10, 0;"
+        : "+r"(y0), "=r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7)
+        : "r"(P::mod(1)), "r"(m), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(y0), "+r"(y1), "+r"(y2), "+r"(y3), "+r"(y4), "+r"(y5), "+r"(y6), "+r"(y7), "+r"(x7)
+        : "r"(P::mod(0)), "r"(m), "r"(P::mod(2)), "r"(P::mod(4)), "r"(P::mod(6)));
+    asm("add.u32 %0, %2, %3;\n\t"
+        "mul.lo.u32 %1, %0, %4;"
+        : "=r"(w), "=r"(m)
+        : "r"(x0), "r"(y1), "r"(P::INV));
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %10, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %10, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %10, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %10, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %10, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %10, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %10, 0;\n\t"
+        "madc.hi.u32 %8, %13, %10, 0;"
+        : "+r"(x0), "=r"(y0), "+r"(y1), "+r"(y2), "+r"(y3), "+r"(y4), "+r"(y5), "+r"(y6), "+r"(y7)
+        : "r"(P::mod(1)), "r"(m), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7), "+r"(y7)
+        : "r"(P::mod(0)), "r"(m), "r"(P::mod(2)), "r"(P::mod(4)), "r"(P::mod(6)));
+    asm("add.u32 %0, %2, %3;\n\t"
+        "mul.lo.u32 %1, %0, %4;"
+        : "=r"(w), "=r"(m)
+        : "r"(y0), "r"(x1), "r"(P::INV));
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %10, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %10, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %10, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %10, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %10, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %10, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %10, 0;\n\t"
+        "madc.hi.u32 %8, %13, %10, 0;"
+        : "+r"(y0), "=r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7)
+        : "r"(P::mod(1)), "r"(m), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(y0), "+r"(y1), "+r"(y2), "+r"(y3), "+r"(y4), "+r"(y5), "+r"(y6), "+r"(y7), "+r"(x7)
+        : "r"(P::mod(0)), "r"(m), "r"(P::mod(2)), "r"(P::mod(4)), "r"(P::mod(6)));
+    asm("add.u32 %0, %2, %3;\n\t"
+        "mul.lo.u32 %1, %0, %4;"
+        : "=r"(w), "=r"(m)
+        : "r"(x0), "r"(y1), "r"(P::INV));
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %10, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %10, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %10, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %10, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %10, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %10, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %10, 0;\n\t"
+        "madc.hi.u32 %8, %13, %10, 0;"
+        : "+r"(x0), "=r"(y0), "+r"(y1), "+r"(y2), "+r"(y3), "+r"(y4), "+r"(y5), "+r"(y6), "+r"(y7)
+        : "r"(P::mod(1)), "r"(m), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7), "+r"(y7)
+        : "r"(P::mod(0)), "r"(m), "r"(P::mod(2)), "r"(P::mod(4)), "r"(P::mod(6)));
+    asm("add.u32 %0, %2, %3;\n\t"
+        "mul.lo.u32 %1, %0, %4;"
+        : "=r"(w), "=r"(m)
+        : "r"(y0), "r"(x1), "r"(P::INV));
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %10, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %10, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %10, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %10, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %10, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %10, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %10, 0;\n\t"
+        "madc.hi.u32 %8, %13, %10, 0;"
+        : "+r"(y0), "=r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7)
+        : "r"(P::mod(1)), "r"(m), "r"(P::mod(3)), "r"(P::mod(5)), "r"(P::mod(7)));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(y0), "+r"(y1), "+r"(y2), "+r"(y3), "+r"(y4), "+r"(y5), "+r"(y6), "+r"(y7), "+r"(x7)
+        : "r"(P::mod(0)), "r"(m), "r"(P::mod(2)), "r"(P::mod(4)), "r"(P::mod(6)));
+    asm("add.cc.u32 %0, %8, %9;\n\t"
+        "addc.cc.u32 %1, %10, %11;\n\t"
+        "addc.cc.u32 %2, %12, %13;\n\t"
+        "addc.cc.u32 %3, %14, %15;\n\t"
+        "addc.cc.u32 %4, %16, %17;\n\t"
+        "addc.cc.u32 %5, %18, %19;\n\t"
+        "addc.cc.u32 %6, %20, %21;\n\t"
+        "addc.u32 %7, %22, 0;"
+        : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7)
+        : "r"(x0), "r"(y1), "r"(x1), "r"(y2), "r"(x2), "r"(y3), "r"(x3), "r"(y4), "r"(x4), "r"(y5), "r"(x5), "r"(y6), "r"(x6), "r"(y7), "r"(x7));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(t0), "+r"(t1), "+r"(t2), "+r"(t3), "+r"(t4), "+r"(t5), "+r"(t6), "+r"(t7)
+        : "r"(T8), "r"(T9), "r"(T10), "r"(T11), "r"(T12), "r"(T13), "r"(T14), "r"(T15));
+    uint32_t t[8] = {t0, t1, t2, t3, t4, t5, t6, t7};
+    return fp_final_sub<P>(t);
+    // ---- end of generated code ----
+#else
     return fp_mul(a, a);
+#endif
 }
 
 template <class P> KZG_HD Fp<P> fp_to_mont(const Fp<P>& a) {

@@ -773,7 +773,7 @@ __device__ __forceinline__ G1Affine load_dense_point(const Fq* xs, const Fq* ys,
 // partial-sum slot of (bucket, slice):  pbase[key] + (slice index - first slice of the bucket).
 // DIRECT: the list is a dense array of points in bucket order (what the batched-affine rounds below leave), not indices.
 template <bool DIRECT>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine* __restrict__ bases,
+__global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const G1Affine* __restrict__ bases,
                                                              const Fq* __restrict__ dense_x, const Fq* __restrict__ dense_y,
                                                              const uint32_t* __restrict__ sorted,
                                                              const uint32_t* __restrict__ offsets,
