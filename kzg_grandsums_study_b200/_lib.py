@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkzgb200.so")
+LIB_PATH = os.environ.get("KZGB200_LIB") or os.path.join(HERE, "libkzgb200.so")  # (override: A/B builds of experiments)
 
 u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p

@@ -31,6 +31,62 @@ class Block:
         self.ins.append(t)
 
 
+def append_redc(blocks, T):
+    """Montgomery reduction of the 16-word T (< 2 p^2 + ...): appends the blocks that leave t0..t7 = T / 2^256 mod p, < 2 p"""
+    # ---- Montgomery reduction of T: U = (T_low + sum m_k p 2^(32 k)) / 2^256 <= p, result = U + T_high < 2 p
+    # pair (lo: positions 0..7, hi: positions 1..8); after each step the total is divisible by 2^32 and the roles swap
+    x = ["x%d" % k for k in range(8)]
+    y = ["y%d" % k for k in range(8)]
+    mod = [("mod", k) for k in range(8)]
+    b = Block()
+    for k in range(8):
+        b.add("mov", x[k], T[k])
+    b.add("mul.lo", "m", x[0], ("inv",))
+    blocks.append(b)
+    b = Block()
+    for n, k in enumerate((1, 3, 5, 7)):   # y = odd limbs of p times m (plain products)
+        b.add("mul.lo", y[2 * n], mod[k], "m")
+        b.add("mul.hi", y[2 * n + 1], mod[k], "m")
+    blocks.append(b)
+
+    def cmad4_top(lo, m, top):
+        b = Block()
+        for n, k in enumerate((0, 2, 4, 6)):
+            b.add(("mad.lo.cc" if n == 0 else "madc.lo.cc"), lo[2 * n], mod[k], m, lo[2 * n])
+            b.add("madc.hi.cc", lo[2 * n + 1], mod[k], m, lo[2 * n + 1])
+        b.add("addc", top, top, 0)
+        blocks.append(b)
+
+    cmad4_top(x, "m", y[7])
+    for i in range(1, 8):
+        lo, hi = (y, x) if i & 1 else (x, y)
+        # the old lo (now `hi`): word 0 is zero, word 1 belongs to the new position 0, words 2..7 become the new hi 0..5
+        b = Block()
+        b.add("addw", "w", lo[0], hi[1])      # wrapping: only the low word decides m
+        b.add("mul.lo", "m", "w", ("inv",))
+        blocks.append(b)
+        b = Block()
+        b.add("add.cc", lo[0], lo[0], hi[1])
+        src = [hi[2], hi[3], hi[4], hi[5], hi[6], hi[7], 0, 0]
+        for n, k in enumerate((1, 3, 5, 7)):
+            b.add("madc.lo.cc", hi[2 * n], mod[k], "m", src[2 * n])
+            b.add("madc.hi" + (".cc" if n < 3 else ""), hi[2 * n + 1], mod[k], "m", src[2 * n + 1])
+        blocks.append(b)
+        cmad4_top(lo, "m", hi[7])
+    # after step 7 (odd): lo = y, hi = x; result word j = hi[j] + lo[j + 1] (lo[0] == 0), then + T_high
+    lo, hi = y, x
+    b = Block()
+    for j in range(8):
+        op = "add.cc" if j == 0 else ("addc.cc" if j < 7 else "addc")
+        b.add(op, "t%d" % j, hi[j], lo[j + 1] if j < 7 else 0)
+    blocks.append(b)
+    b = Block()
+    for j in range(8):
+        op = "add.cc" if j == 0 else ("addc.cc" if j < 7 else "addc")
+        b.add(op, "t%d" % j, "t%d" % j, T[8 + j])
+    blocks.append(b)
+
+
 def build():
     """-> list of Blocks; variables: a0..a7 (inputs), t0..t7 (result before the final subtraction)."""
     blocks = []
@@ -133,58 +189,7 @@ def build():
             b.add("madc.hi" + (".cc" if i < 7 else ""), T[2 * i + 1], a[i], a[i], D[2 * i + 1])
     blocks.append(b)
 
-    # ---- Montgomery reduction of T: U = (T_low + sum m_k p 2^(32 k)) / 2^256 <= p, result = U + T_high < 2 p
-    # pair (lo: positions 0..7, hi: positions 1..8); after each step the total is divisible by 2^32 and the roles swap
-    x = ["x%d" % k for k in range(8)]
-    y = ["y%d" % k for k in range(8)]
-    mod = [("mod", k) for k in range(8)]
-    b = Block()
-    for k in range(8):
-        b.add("mov", x[k], T[k])
-    b.add("mul.lo", "m", x[0], ("inv",))
-    blocks.append(b)
-    b = Block()
-    for n, k in enumerate((1, 3, 5, 7)):   # y = odd limbs of p times m (plain products)
-        b.add("mul.lo", y[2 * n], mod[k], "m")
-        b.add("mul.hi", y[2 * n + 1], mod[k], "m")
-    blocks.append(b)
-
-    def cmad4_top(lo, m, top):
-        b = Block()
-        for n, k in enumerate((0, 2, 4, 6)):
-            b.add(("mad.lo.cc" if n == 0 else "madc.lo.cc"), lo[2 * n], mod[k], m, lo[2 * n])
-            b.add("madc.hi.cc", lo[2 * n + 1], mod[k], m, lo[2 * n + 1])
-        b.add("addc", top, top, 0)
-        blocks.append(b)
-
-    cmad4_top(x, "m", y[7])
-    for i in range(1, 8):
-        lo, hi = (y, x) if i & 1 else (x, y)
-        # the old lo (now `hi`): word 0 is zero, word 1 belongs to the new position 0, words 2..7 become the new hi 0..5
-        b = Block()
-        b.add("addw", "w", lo[0], hi[1])      # wrapping: only the low word decides m
-        b.add("mul.lo", "m", "w", ("inv",))
-        blocks.append(b)
-        b = Block()
-        b.add("add.cc", lo[0], lo[0], hi[1])
-        src = [hi[2], hi[3], hi[4], hi[5], hi[6], hi[7], 0, 0]
-        for n, k in enumerate((1, 3, 5, 7)):
-            b.add("madc.lo.cc", hi[2 * n], mod[k], "m", src[2 * n])
-            b.add("madc.hi" + (".cc" if n < 3 else ""), hi[2 * n + 1], mod[k], "m", src[2 * n + 1])
-        blocks.append(b)
-        cmad4_top(lo, "m", hi[7])
-    # after step 7 (odd): lo = y, hi = x; result word j = hi[j] + lo[j + 1] (lo[0] == 0), then + T_high
-    lo, hi = y, x
-    b = Block()
-    for j in range(8):
-        op = "add.cc" if j == 0 else ("addc.cc" if j < 7 else "addc")
-        b.add(op, "t%d" % j, hi[j], lo[j + 1] if j < 7 else 0)
-    blocks.append(b)
-    b = Block()
-    for j in range(8):
-        op = "add.cc" if j == 0 else ("addc.cc" if j < 7 else "addc")
-        b.add(op, "t%d" % j, "t%d" % j, T[8 + j])
-    blocks.append(b)
+    append_redc(blocks, T)
     return blocks
 
 
@@ -286,17 +291,19 @@ def check():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def emit():
-    blocks = build()
+def emit(blocks=None, inputs=("a",)):
+    if blocks is None:
+        blocks = build()
     out = []
-    declared = set("a%d" % i for i in range(8))
+    declared = set("%s%d" % (nm, i) for nm in inputs for i in range(8))
     decl = []
     for b in blocks:
         for t in b.ins:
             if t[1] not in declared:
                 declared.add(t[1])
                 decl.append(t[1])
-    out.append("    const uint32_t " + ", ".join("a%d = a.l[%d]" % (i, i) for i in range(8)) + ";")
+    for nm in inputs:
+        out.append("    const uint32_t " + ", ".join("%s%d = %s.l[%d]" % (nm, i, nm, i) for i in range(8)) + ";")
     line = "    uint32_t "
     cur = line
     for i, d in enumerate(decl):
@@ -342,6 +349,10 @@ def emit():
             name = {"shf.l": "shf.l.wrap.b32", "mov": "mov.b32"}.get(op, op + ".u32")
             if op == "addw":
                 name = "add.u32"
+            if op == "and":
+                name = "and.b32"
+            if op == "neg":
+                name = "neg.s32"
             if op == "shr31":
                 name, args = "shr.u32", [ref(t[1]), ref(t[2]), "31"]
             elif op == "shl1":
@@ -366,24 +377,20 @@ BEGIN = "// ---- GENERATED by tools/gen_fp_sqr.py (do not edit by hand) ----"
 END = "// ---- end of generated code ----"
 
 
+BEGIN_K = "// ---- GENERATED by tools/gen_fp_sqr.py: Karatsuba product (do not edit by hand) ----"
+END_K = "// ---- end of the generated Karatsuba product ----"
+
+
 def update():
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kzg_grandsums_study_b200", "csrc", "field.cuh")
     s = open(path).read()
     i, j = s.index(BEGIN), s.index(END)
     s = s[:i] + BEGIN + "\n" + emit() + "\n    " + s[j:]
+    if BEGIN_K in s:
+        i, j = s.index(BEGIN_K), s.index(END_K)
+        s = s[:i] + BEGIN_K + "\n" + emit(build_mulk(), inputs=("a", "b")) + "\n    " + s[j:]
     open(path, "w").write(s)
     print("updated", path)
-
-
-if __name__ == "__main__":
-    cmd = sys.argv[1] if len(sys.argv) > 1 else "check"
-    if cmd == "check":
-        check()
-    elif cmd == "emit":
-        print(emit())
-    elif cmd == "update":
-        check()
-        update()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -504,13 +511,32 @@ def emulate_named(blocks, vals, p):
                     r += cf
                 out_c = r >> 32
                 r &= M32
+            elif base in ("sub", "subc"):
+                r = s[0] - s[1]
+                if base == "subc":
+                    assert cf is not None
+                    r -= cf
+                out_c = 1 if r < 0 else 0   # the borrow
+                r &= M32
+            elif base == "and":
+                r = s[0] & s[1]
+                out_c = None
+            elif base == "neg":
+                r = (-s[0]) & M32
+                out_c = None
+            elif base == "mov":
+                r = s[0]
+                out_c = None
+            elif base == "addw":
+                r = (s[0] + s[1]) & M32
+                out_c = None
             else:
                 raise ValueError(op)
             if cc_out:
                 cf = out_c
             elif out_c:
                 raise AssertionError(("carry lost", t))
-            if not cc_out and base in ("madc", "addc"):
+            if not cc_out and base in ("madc", "addc", "subc"):
                 cf = None
             v[dst] = r
     return sum(v["t%d" % j] << (32 * j) for j in range(8))
@@ -541,5 +567,151 @@ def check_mul2():
     print("fp_mul2 helper sequence: %d operand tuples per field ok; largest result %.3f p (< 3 p)" % (len(cases), worst / 1000))
 
 
-if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "check2":
-    check_mul2()
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp_mulk(a, b): Karatsuba 8 x 8 limbs (three 4 x 4 products = 48 wide MACs) + the separated reduction above (64):
+# 112 wide MACs instead of 128, paid for with ~70 more additions on the (mostly idle) ALU pipe.
+#   a b = z0 + ((aL + aH)(bL + bH) - z0 - z2) 2^128 + z2 2^256
+# Every 4 x 4 product uses the even / odd accumulator pair (E: even limb positions, O: odd) so that a row is two carry
+# chains of two word pairs; a chain's carry lands in a word that holds nothing but carries so far.
+def mac_chain(blocks, written, acc, base, prods, carry_to):
+    """acc[base + 2 n], acc[base + 2 n + 1] += x_n * y_n for (x_n, y_n) in prods, one carry chain; carry -> acc[carry_to]"""
+    b = Block()
+    nocarry = True
+    for n, (xv, yv) in enumerate(prods):
+        for k, part in ((0, "lo"), (1, "hi")):
+            word = acc[base + 2 * n + k]
+            addend = word if word in written else 0
+            last = n == len(prods) - 1 and part == "hi"
+            cc_out = not (last and carry_to is None)
+            if nocarry:
+                if addend == 0:
+                    b.add("mul." + part, word, xv, yv)
+                else:
+                    b.add("mad.%s%s" % (part, ".cc" if cc_out else ""), word, xv, yv, addend)
+                    nocarry = False
+            else:
+                b.add("madc.%s%s" % (part, ".cc" if cc_out else ""), word, xv, yv, addend)
+            written.add(word)
+    if carry_to is not None:
+        w = acc[carry_to]
+        assert w not in written and not nocarry
+        b.add("addc", w, 0, 0)
+        written.add(w)
+    blocks.append(b)
+
+
+def subprod(blocks, x, y, name):
+    """-> names of the 8 words of x[0..3] * y[0..3]"""
+    E = ["%se%d" % (name, k) for k in range(8)]
+    O = ["%so%d" % (name, k) for k in range(7)]     # O[k] = word position k + 1
+    w = set()
+    mac_chain(blocks, w, E, 0, [(x[0], y[0]), (x[2], y[0])], None)
+    mac_chain(blocks, w, O, 0, [(x[1], y[0]), (x[3], y[0])], None)
+    mac_chain(blocks, w, O, 0, [(x[0], y[1]), (x[2], y[1])], 4)
+    mac_chain(blocks, w, E, 2, [(x[1], y[1]), (x[3], y[1])], None)
+    mac_chain(blocks, w, E, 2, [(x[0], y[2]), (x[2], y[2])], 6)
+    mac_chain(blocks, w, O, 2, [(x[1], y[2]), (x[3], y[2])], None)
+    mac_chain(blocks, w, O, 2, [(x[0], y[3]), (x[2], y[3])], 6)
+    mac_chain(blocks, w, E, 4, [(x[1], y[3]), (x[3], y[3])], None)
+    assert w == set(E) | set(O)
+    b = Block()
+    for k in range(1, 8):
+        b.add("add.cc" if k == 1 else ("addc.cc" if k < 7 else "addc"), E[k], E[k], O[k - 1])
+    blocks.append(b)
+    return E
+
+
+def build_mulk():
+    blocks = []
+    a = ["a%d" % i for i in range(8)]
+    bb = ["b%d" % i for i in range(8)]
+    z0 = subprod(blocks, a[:4], bb[:4], "p")
+    z2 = subprod(blocks, a[4:], bb[4:], "q")
+    sa = ["sa%d" % i for i in range(4)]
+    sb = ["sb%d" % i for i in range(4)]
+    for sv, v, cv in ((sa, a, "ca"), (sb, bb, "cb")):
+        b = Block()
+        for i in range(4):
+            b.add("add.cc" if i == 0 else "addc.cc", sv[i], v[i], v[4 + i])
+        b.add("addc", cv, 0, 0)
+        blocks.append(b)
+    zm = subprod(blocks, sa, sb, "m") + ["zm8"]
+    b = Block()
+    b.add("and", "zm8", "ca", "cb")
+    b.add("neg", "na", "ca")
+    b.add("neg", "nb", "cb")
+    for i in range(4):
+        b.add("and", "ta%d" % i, sb[i], "na")
+        b.add("and", "tb%d" % i, sa[i], "nb")
+    blocks.append(b)
+    for tv in ("ta", "tb"):     # zm += (ca sb + cb sa) 2^128
+        b = Block()
+        for i in range(4):
+            b.add("add.cc" if i == 0 else "addc.cc", zm[4 + i], zm[4 + i], "%s%d" % (tv, i))
+        b.add("addc", "zm8", "zm8", 0)
+        blocks.append(b)
+    for z in (z0, z2):          # zm -= z0, zm -= z2 (never negative)
+        b = Block()
+        for i in range(8):
+            b.add("sub.cc" if i == 0 else "subc.cc", zm[i], zm[i], z[i])
+        b.add("subc", "zm8", "zm8", 0)
+        blocks.append(b)
+    T = z0 + z2
+    b = Block()
+    for i in range(9):
+        b.add("add.cc" if i == 0 else "addc.cc", T[4 + i], T[4 + i], zm[i])
+    b.add("addc.cc", T[13], T[13], 0)
+    b.add("addc.cc", T[14], T[14], 0)
+    b.add("addc", T[15], T[15], 0)
+    blocks.append(b)
+    append_redc(blocks, T)
+    return blocks
+
+
+def check_mulk():
+    blocks = build_mulk()
+    n_wide = sum(1 for b in blocks for t in b.ins
+                 if t[0].startswith(("mad", "mul")) and not (isinstance(t[3], tuple) and t[3][0] == "inv"))
+    n_all = sum(len(b.ins) for b in blocks)
+    n_mov = sum(1 for b in blocks for t in b.ins if t[0] == "mov")
+    print("fp_mulk: %d wide MACs, %d other instructions (+ %d register moves)" % (n_wide // 2, n_all - n_wide - n_mov, n_mov))
+    rng = random.Random(13)
+    for p in (Q, R_):
+        rinv = pow(1 << 256, -1, p)
+        edge = [0, 1, p - 1, p - 2, (1 << 253) - 1, p >> 1, M32, (1 << 128) - 1, ((1 << 128) - 1) << 128 & ((1 << 253) - 1),
+                sum(M32 << (32 * i) for i in range(8)) % p, (1 << 128), (1 << 127) | (1 << 253) % p]
+        cases = [(x_, y_) for x_ in edge for y_ in edge]
+        cases += [(rng.randrange(p), rng.randrange(p)) for _ in range(20000)]
+        for _ in range(6000):
+            ops = []
+            for _k in range(2):
+                a_ = 0
+                for i in range(8):
+                    a_ |= rng.choice((0, M32, 1, 0x80000000, 0xFFFFFFFE, rng.randrange(1 << 32))) << (32 * i)
+                ops.append(a_ % p)
+            cases.append(tuple(ops))
+        for (a_, b_) in cases:
+            t = emulate_named(blocks, {"a": a_, "b": b_}, p)
+            assert t % p == a_ * b_ * rinv % p and t < 2 * p, (hex(a_), hex(b_), hex(t))
+    print("fp_mulk instruction list: %d operand pairs per field ok" % len(cases))
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1] if len(sys.argv) > 1 else "check"
+    if cmd == "check":
+        check()
+        check_mul2()
+        check_mulk()
+    elif cmd == "check2":
+        check_mul2()
+    elif cmd == "checkk":
+        check_mulk()
+    elif cmd == "emit":
+        print(emit())
+    elif cmd == "emitk":
+        print(emit(build_mulk(), inputs=("a", "b")))
+    elif cmd == "update":
+        check()
+        check_mulk()
+        update()
