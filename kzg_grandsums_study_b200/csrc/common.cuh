@@ -23,7 +23,7 @@ struct MsmTuning {
     int red_k0 = -1;                // log2 of the level-0 radix of the bucket reduction; -1: by size
     int tail_width = 0;             // threads per tail task (32 / 64 / 128); 0: by size
     int host_cut_a = 0, host_cut_b = 64;  // host-scalar MSM: piece cuts at a/64 and b/64 of the points; 0: default
-    int host_link = 1;              // the two pieces of a host-scalar MSM share one bucket reduction (1: below 2^24 points, 2: always, 0: one each)
+    int host_link = 1;              // the pieces of a host-scalar MSM over a window table share one bucket reduction (0: one each)
     uint32_t host_piece_min_log = 21;     // ... pieces from 2^this points on (2^21: the 8-GPU shard, 8.3 -> 7.5 ms e2e)
     int split_min_log = -1, split_max_log = -1;  // two-lane split of ONE msm (off: measured slower since the affine rounds)
     int merge = 1;                  // commitments of one round over one table as one merged pipeline
@@ -77,6 +77,9 @@ struct kzg_ctx {
     size_t scratch_bytes = 0;
     void* scratch2 = nullptr;
     size_t scratch2_bytes = 0;
+    void* scratch3 = nullptr;       // third arena: the first of three linked pieces of a host-scalar MSM (its bucket sums must
+    size_t scratch3_bytes = 0;      // outlive the third piece, which runs in lane 0's arena)
+    int arena = -1;                 // arena of the next ctx_scratch call; -1: the lane's own
     // pinned host staging for small results
     uint8_t* pinned = nullptr;
     size_t pinned_bytes = 0;

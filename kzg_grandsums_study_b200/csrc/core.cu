@@ -26,6 +26,8 @@ int ctx_set_option(kzg_ctx* ctx, const char* name, long long value) {
     else if (k == "part_sort") t.part_sort = reset ? def.part_sort : (int)value;
     else if (k == "red_k0") t.red_k0 = reset ? def.red_k0 : (int)value;
     else if (k == "tail_width") t.tail_width = reset ? def.tail_width : (int)value;
+    else if (k == "host_cut_a") t.host_cut_a = reset ? def.host_cut_a : (int)value;
+    else if (k == "host_cut_b") t.host_cut_b = reset ? def.host_cut_b : (int)value;
     else if (k == "host_link") t.host_link = reset ? def.host_link : (int)value;
     else if (k == "host_piece_min_log") t.host_piece_min_log = reset ? def.host_piece_min_log : (uint32_t)value;
     else if (k == "split_min_log") t.split_min_log = reset ? def.split_min_log : (int)value;
@@ -108,8 +110,9 @@ __global__ void __launch_bounds__(256) modmul_peak_kernel(uint32_t iters, uint32
 }
 
 int ctx_scratch(kzg_ctx* ctx, size_t bytes, void** out) {
-    void*& arena = ctx->lane == 0 ? ctx->scratch : ctx->scratch2;
-    size_t& arena_bytes = ctx->lane == 0 ? ctx->scratch_bytes : ctx->scratch2_bytes;
+    const int which = ctx->arena >= 0 ? ctx->arena : ctx->lane;
+    void*& arena = which == 0 ? ctx->scratch : which == 1 ? ctx->scratch2 : ctx->scratch3;
+    size_t& arena_bytes = which == 0 ? ctx->scratch_bytes : which == 1 ? ctx->scratch2_bytes : ctx->scratch3_bytes;
     if (bytes > arena_bytes) {
         // free the old block once its lane is idle, then a fresh (larger) one; rounded up to limit regrowth
         if (arena) {
@@ -384,6 +387,7 @@ int kzg_ctx_destroy(kzg_ctx* ctx) {
     for (auto& t : ctx->coset_tables) cudaFree(t.inv_nx);
     cudaFree(ctx->scratch);
     cudaFree(ctx->scratch2);
+    cudaFree(ctx->scratch3);
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);

@@ -1253,6 +1253,8 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_reduce_level0_kernel(const
                                                                            const uint32_t* __restrict__ pbase,
                                                                            const G1XYZZ* __restrict__ in2,
                                                                            const uint32_t* __restrict__ pbase2,
+                                                                           const G1XYZZ* __restrict__ in3,
+                                                                           const uint32_t* __restrict__ pbase3,
                                                                            uint32_t nbuckets, uint32_t radix,
                                                                            G1XYZZ* __restrict__ out_u, uint32_t n_out,
                                                                            G1XYZZ* __restrict__ out_t) {
@@ -1274,6 +1276,13 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_reduce_level0_kernel(const
             const uint32_t a2 = pbase2[key];
             if (pbase2[key + 1] != a2) {
                 G1XYZZ o = load_xyzz(in2 + a2);
+                xyzz_add_fn(run, o);
+            }
+        }
+        if (in3) {
+            const uint32_t a3 = pbase3[key];
+            if (pbase3[key + 1] != a3) {
+                G1XYZZ o = load_xyzz(in3 + a3);
                 xyzz_add_fn(run, o);
             }
         }
@@ -1633,7 +1642,7 @@ cudaEvent_t order_event(kzg_ctx* ctx) {
 // `jobs.count` MSMs over the same bases as one pipeline; results[j] receives the XYZZ sum of job j (device memory).
 // More than one job needs the window-table flavour.
 int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XYZZ* results, const MsmReduceLink* add_in,
-                  MsmReduceLink* defer_out) {
+                  uint32_t n_add_in, MsmReduceLink* defer_out) {
     const uint32_t njobs = jobs.count;
     if (njobs == 0) return KZG_OK;
     if (njobs > MSM_MAX_JOBS) return set_err(ctx, KZG_ERR_ARG, "msm: too many jobs in one pipeline");
@@ -2000,13 +2009,14 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
         KZG_CHECK_LAUNCH(ctx);
         return KZG_OK;
     }
-    const G1XYZZ* in2 = nullptr;
-    const uint32_t* pbase2 = nullptr;
-    if (add_in) {
-        if (add_in->nkeys != nkeys) return set_err(ctx, KZG_ERR_ARG, "msm: linked pieces must share the bucket geometry");
-        KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, add_in->ready, 0));
-        in2 = add_in->partials;
-        pbase2 = add_in->pbase;
+    const G1XYZZ* in_more[2] = {nullptr, nullptr};
+    const uint32_t* pbase_more[2] = {nullptr, nullptr};
+    if (n_add_in > 2) return set_err(ctx, KZG_ERR_ARG, "msm: at most two earlier pieces per reduction");
+    for (uint32_t k = 0; k < n_add_in; k++) {
+        if (add_in[k].nkeys != nkeys) return set_err(ctx, KZG_ERR_ARG, "msm: linked pieces must share the bucket geometry");
+        KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, add_in[k].ready, 0));
+        in_more[k] = add_in[k].partials;
+        pbase_more[k] = add_in[k].pbase;
     }
     // table flavour: every bucket set IS a result (one per job); raw flavour: the sets are the windows of one result
     G1XYZZ* sums_out = g.table ? results : set_sums;
@@ -2014,7 +2024,7 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
         const dim3 grid((tg.n1 + RED_THREADS - 1) / RED_THREADS, g.nsets);
         // (measured: calling the shared addition at 126 registers / 16 warps per SM beats the inlined 168-register
         // version with its spills: 0.60 vs 0.66 ms for the whole reduction at 2^19 buckets)
-        KZG_LAUNCH(ctx, msm_reduce_level0_kernel, grid, RED_THREADS, 0, partials, segoff, in2, pbase2, g.nbuckets, 1u << tg.k0, u_arrays, tg.n1,
+        KZG_LAUNCH(ctx, msm_reduce_level0_kernel, grid, RED_THREADS, 0, partials, segoff, in_more[0], pbase_more[0], in_more[1], pbase_more[1], g.nbuckets, 1u << tg.k0, u_arrays, tg.n1,
                    tvals);
     }
     {
@@ -2054,18 +2064,18 @@ int msm_run(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G
     jobs.n[0] = n;
     jobs.montgomery = src.montgomery ? 1u : 0u;
     jobs.count = 1;
-    return msm_run_multi(ctx, bases, jobs, result_dev, nullptr, nullptr);
+    return msm_run_multi(ctx, bases, jobs, result_dev, nullptr, 0, nullptr);
 }
 // one piece of a linked pair (see MsmReduceLink)
 static int msm_run_linked(kzg_ctx* ctx, const MsmBases& bases, MsmScalarSrc src, uint64_t n, G1XYZZ* result_dev,
-                          const MsmReduceLink* add_in, MsmReduceLink* defer_out) {
+                          const MsmReduceLink* add_in, uint32_t n_add_in, MsmReduceLink* defer_out) {
     MsmJobs jobs;
     memset(&jobs, 0, sizeof(jobs));
     jobs.scalars[0] = src.scalars;
     jobs.n[0] = n;
     jobs.montgomery = src.montgomery ? 1u : 0u;
     jobs.count = 1;
-    return msm_run_multi(ctx, bases, jobs, result_dev, add_in, defer_out);
+    return msm_run_multi(ctx, bases, jobs, result_dev, add_in, n_add_in, defer_out);
 }
 
 int msm_result_to_host_affine(kzg_ctx* ctx, const G1XYZZ* result_dev, uint32_t count, uint8_t out[64]) {
@@ -2183,7 +2193,7 @@ int msm_run_batch(kzg_ctx* ctx, const MsmJob* jobs, uint32_t count, uint8_t* out
             mj.n[j] = jobs[gr.first + j].n;
             if (jobs[gr.first + j].src.montgomery) mj.montgomery |= 1u << j;
         }
-        r = msm_run_multi(ctx, jobs[gr.first].bases, mj, xyzz_slots + gr.first, nullptr, nullptr);
+        r = msm_run_multi(ctx, jobs[gr.first].bases, mj, xyzz_slots + gr.first, nullptr, 0, nullptr);
         if (r == KZG_OK) {
             KZG_LAUNCH(ctx, g1_finish_many_kernel, gr.count, 32, 0, xyzz_slots + gr.first, affine_slots + gr.first);
             if (cudaGetLastError() != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, "g1_finish launch failed");
@@ -2384,12 +2394,24 @@ static int srs_msm_host_pieces(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const
         // Without a table (per-window bucket sets whose geometry depends on the piece size) every piece reduces on its
         // own: three pieces of 1/8, 2/8, 5/8.
         const bool table_flavour = srs->table && ctx->msm_window == 0;
+        const bool lanes = ctx->lane == 0 && !ctx->no_split;
         uint64_t cut[4] = {0, n / 8, n / 8 + n / 4, n};
         parts = 3;
         if (table_flavour) {
             parts = 2;
             cut[1] = n / 16 * 3;
             cut[2] = n;
+            // With two pieces the step is (upload of everything) + (MSM of the last 13/16): the last piece cannot start
+            // before the whole upload has arrived (10 ms for 512 MiB), and the GPU idles once the first piece is done.
+            // Three linked pieces (1/16, 4/16, 11/16) keep it busy during the upload and leave a smaller rest: e2e 37.2 ->
+            // 36.3 ms at 2^24 points, 10.75 -> 10.33 at 2^22, no difference at 2^23 (20.3).  What remains above the
+            // resident-scalar MSM (32.8 ms) is the first upload (0.65 ms) and the pieces' own inefficiency: two more sorts,
+            // fewer affine rounds in the small pieces, one more addition per bucket and piece in the shared reduction.
+            if (n >= (1ull << 22) && lanes && ctx->tuning.host_link) {
+                parts = 3;
+                cut[1] = n / 16;
+                cut[2] = n / 16 * 5;
+            }
         }
         if (ctx->tuning.host_cut_a > 0) {  // tuning: cuts at a/64 and b/64 of n (b = 64: two pieces)
             const int a = ctx->tuning.host_cut_a, b = ctx->tuning.host_cut_b;
@@ -2412,14 +2434,11 @@ static int srs_msm_host_pieces(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const
             if (e == cudaSuccess) e = cudaEventRecord(up[k], ctx->copy_stream);
         }
         if (e != cudaSuccess) r = set_err(ctx, KZG_ERR_CUDA, std::string("msm upload: ") + cudaGetErrorString(e));
-        const bool lanes = ctx->lane == 0 && !ctx->no_split;
-        // (measured, e2e ms with / without: 6.05 / 6.57 at 2^21 points, 11.03 / 12.37 at 2^22, 20.71 / 21.06 at 2^23, but
-        // 37.76 / 37.50 at 2^24 -- there the second piece cannot start before its 416 MiB upload ends, the first piece's own
-        // reduction hides under that wait, and the shared one pays a third addition per bucket: host_link = 1 links below
-        // 2^24 points, 2 always, 0 never)
-        const bool link_wanted = ctx->tuning.host_link == 2 || (ctx->tuning.host_link == 1 && n < (1ull << 24));
-        const bool link = parts == 2 && lanes && table_flavour && link_wanted && cut[1] > 0 && cut[1] < n;
-        MsmReduceLink lk;
+        // (measured, e2e ms linked / each piece reducing on its own: 6.05 / 6.57 at 2^21 points, 11.03 / 12.37 at 2^22,
+        // 20.71 / 21.06 at 2^23 with two pieces; host_link = 0: never)
+        bool link = lanes && table_flavour && ctx->tuning.host_link != 0;
+        for (uint32_t k = 0; k + 1 < parts; k++) link = link && cut[k + 1] > cut[k] && cut[k + 1] < n;
+        MsmReduceLink lk[2];
         for (uint32_t k = 0; k < parts && r == KZG_OK; k++) {
             const int lane = lanes ? (int)(k & 1) : 0;
             ctx->lane = lane;
@@ -2427,10 +2446,17 @@ static int srs_msm_host_pieces(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const
             cudaStreamWaitEvent(ctx->stream, up[k], 0);
             const MsmBases pb = srs_bases(ctx, srs, first + cut[k]);
             const MsmScalarSrc ps{tmp + cut[k], false};
-            if (link)  // piece 0 (lane 0's arena) stops after its fold, piece 1 (lane 1's arena) reduces both
-                r = msm_run_linked(ctx, pb, ps, cut[k + 1] - cut[k], slots, k == 0 ? nullptr : &lk, k == 0 ? &lk : nullptr);
-            else
+            if (link) {
+                // every piece but the last stops after its fold; the last one reduces all of them.  The bucket sums of a
+                // piece live in its scratch arena until then: of three pieces the first and the last share lane 0 (one
+                // stream), so the first one works in the third arena.
+                const bool last = k + 1 == parts;
+                if (parts == 3 && k == 0) ctx->arena = 2;
+                r = msm_run_linked(ctx, pb, ps, cut[k + 1] - cut[k], slots, last ? lk : nullptr, last ? k : 0, last ? nullptr : &lk[k]);
+                ctx->arena = -1;
+            } else {
                 r = msm_run(ctx, pb, ps, cut[k + 1] - cut[k], slots + k);
+            }
         }
         if (link) parts = 1;
         ctx->lane = 0;

@@ -225,12 +225,13 @@ def test_two_contexts_on_two_devices(tau):
         b.terminate()
 
 
-@pytest.mark.parametrize("log_n,table_c", [(21, 0), (22, 0), (21, 14)])
-def test_host_scalar_pieces_share_one_reduction(curve, tau, log_n, table_c):
-    """kzg_srs_msm_host cuts the scalars into two pieces whose uploads hide behind compute; with a window table the first
-    piece hands its folded bucket sums to the second piece's reduction (host_link = 1, default) instead of reducing on its
-    own (0).  Same point either way, equal to the resident-scalar MSM -- also with skewed scalars whose buckets are empty
-    in one piece and full in the other."""
+@pytest.mark.parametrize("log_n,table_c,cuts", [(21, 0, None), (22, 0, None), (21, 14, None), (21, 0, (4, 20)), (21, 13, (9, 10))])
+def test_host_scalar_pieces_share_one_reduction(curve, tau, log_n, table_c, cuts):
+    """kzg_srs_msm_host cuts the scalars into two pieces (three from 2^24 points on; forced here with the cut knobs: at
+    a / 64 and b / 64 of the points) whose uploads hide behind compute; with a window table every piece but the last hands
+    its folded bucket sums to the last piece's reduction (host_link = 1, default) instead of reducing on its own (0).
+    Same point either way, equal to the resident-scalar MSM -- also with skewed scalars whose buckets are empty in one
+    piece and full in the other."""
     import torch
     from kzg_grandsums_study_b200 import synthetic
     from kzg_grandsums_study_b200._lib import as_ptr
@@ -247,11 +248,16 @@ def test_host_scalar_pieces_share_one_reduction(curve, tau, log_n, table_c):
             dev = curve.to_device(data.tobytes())
             want = bytearray(64)
             curve.check(lib.kzg_srs_msm(ctx, srs, 0, dev.handle, n, as_ptr(want)))
-            for link in (1, 2, 0):              # by size (links at these sizes) / always / never
+            for link in (1, 0):
                 curve.set_option("host_link", link)
+                if cuts:
+                    curve.set_option("host_cut_a", cuts[0])
+                    curve.set_option("host_cut_b", cuts[1])
                 got = bytearray(64)
                 curve.check(lib.kzg_srs_msm_host(ctx, srs, 0, as_ptr(host), n, as_ptr(got)))
                 assert bytes(got) == bytes(want), (log_n, table_c, link)
     finally:
         curve.set_option("host_link", -1)
+        curve.set_option("host_cut_a", -1)
+        curve.set_option("host_cut_b", -1)
         curve.lib.kzg_srs_free(curve.ctx, srs)
