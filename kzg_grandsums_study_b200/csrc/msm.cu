@@ -92,7 +92,7 @@ struct MsmJobs {
 };
 
 // One piece of an MSM handing its folded bucket sums (one point per non-empty bucket, addressed through pbase) to the
-// reduction of a later piece over the same bucket geometry; `ready` is recorded on the producing stream after the fold.
+// later pieces over the same bucket geometry (MsmCarry); `ready` is recorded on the producing stream after the fold.
 struct MsmReduceLink {
     const G1XYZZ* partials = nullptr;
     const uint32_t* pbase = nullptr;
@@ -756,6 +756,26 @@ __device__ __forceinline__ G1XYZZ load_xyzz(const G1XYZZ* p) {
     return v;
 }
 
+// Bucket sums of EARLIER pieces of the same MSM over the same bucket geometry (a host-scalar MSM is cut into pieces so
+// that its uploads hide behind compute), latest piece first.  A piece starts every bucket of its walk from the sum the
+// latest earlier piece left for it -- which already contains the pieces before that one -- so merging the pieces costs
+// no group operation at all; a bucket that is empty in this piece is picked up by the reduction the same way.
+struct MsmCarry {
+    const G1XYZZ* in[2];
+    const uint32_t* pbase[2];
+};
+__device__ __forceinline__ G1XYZZ load_xyzz(const G1XYZZ* p);
+__device__ __noinline__ G1XYZZ carry_point(const MsmCarry& cy, uint32_t key) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (cy.in[k]) {
+            const uint32_t a = cy.pbase[k][key];
+            if (cy.pbase[k][key + 1] != a) return load_xyzz(cy.in[k] + a);
+        }
+    }
+    return xyzz_inf();
+}
+
 __device__ __forceinline__ G1Affine load_dense_point(const Fq* xs, const Fq* ys, uint32_t i) {
     G1Affine r;
     const uint4* qx = reinterpret_cast<const uint4*>(xs + i);
@@ -772,13 +792,14 @@ __device__ __forceinline__ G1Affine load_dense_point(const Fq* xs, const Fq* ys,
 // the bucket sizes fluctuate.  Whenever the walk crosses a bucket boundary the running sum is parked in the
 // partial-sum slot of (bucket, slice):  pbase[key] + (slice index - first slice of the bucket).
 // DIRECT: the list is a dense array of points in bucket order (what the batched-affine rounds below leave), not indices.
-template <bool DIRECT>
+// CARRY: the walk opens every bucket with the sum earlier pieces of the same MSM left for it (MsmCarry).
+template <bool DIRECT, bool CARRY>
 __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const G1Affine* __restrict__ bases,
                                                              const Fq* __restrict__ dense_x, const Fq* __restrict__ dense_y,
                                                              const uint32_t* __restrict__ sorted,
                                                              const uint32_t* __restrict__ offsets,
                                                              const uint32_t* __restrict__ pbase, uint32_t nkeys,
-                                                             uint32_t slice, G1XYZZ* __restrict__ partials) {
+                                                             uint32_t slice, G1XYZZ* __restrict__ partials, MsmCarry cy) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total = offsets[nkeys];
     const uint64_t begin64 = (uint64_t)t * slice;
@@ -796,6 +817,7 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const G1Affine* 
     uint32_t key_end = offsets[key + 1];
 
     G1XYZZ acc = xyzz_inf();
+    if (CARRY && begin == offsets[key]) acc = carry_point(cy, key);  // this slice opens its bucket
     uint32_t e = DIRECT ? begin : sorted[begin];
 #ifdef KZG_BOUNDS_CHECK
     for (uint32_t j = begin; j < end; j++) {  // every operand of the slice, before anything is fetched
@@ -813,6 +835,7 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const G1Affine* 
                 key++;
                 key_end = offsets[key + 1];
             } while (key_end <= j);
+            if (CARRY) acc = carry_point(cy, key);
         }
         // prefetch the next entry while this one is being added
         uint32_t e_next = e;
@@ -1247,15 +1270,11 @@ __global__ void __launch_bounds__(512) msm_collapse_huge_kernel(G1XYZZ* __restri
 
 // level 0 reads the accumulate output through pbase: one point per bucket (msm_fold / msm_collapse have folded the
 // partial sums of a bucket into its first slot), none for an empty bucket
-// (in2 / pbase2: the bucket points of an earlier piece of the same MSM over the same bucket geometry -- a host-scalar MSM
-// is cut into pieces so that its uploads hide behind compute; the pieces share THIS reduction instead of paying one each)
+// (cy: the bucket sums of earlier pieces of the same MSM, MsmCarry -- the pieces share THIS reduction instead of paying
+// one each)
 __global__ void __launch_bounds__(RED_THREADS, 4) msm_reduce_level0_kernel(const G1XYZZ* __restrict__ in,
                                                                            const uint32_t* __restrict__ pbase,
-                                                                           const G1XYZZ* __restrict__ in2,
-                                                                           const uint32_t* __restrict__ pbase2,
-                                                                           const G1XYZZ* __restrict__ in3,
-                                                                           const uint32_t* __restrict__ pbase3,
-                                                                           uint32_t nbuckets, uint32_t radix,
+                                                                           MsmCarry cy, uint32_t nbuckets, uint32_t radix,
                                                                            G1XYZZ* __restrict__ out_u, uint32_t n_out,
                                                                            G1XYZZ* __restrict__ out_t) {
     const uint32_t set = blockIdx.y;
@@ -1271,20 +1290,9 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_reduce_level0_kernel(const
         if (pbase[key + 1] != a) {
             G1XYZZ o = load_xyzz(in + a);
             xyzz_add_fn(run, o);
-        }
-        if (in2) {
-            const uint32_t a2 = pbase2[key];
-            if (pbase2[key + 1] != a2) {
-                G1XYZZ o = load_xyzz(in2 + a2);
-                xyzz_add_fn(run, o);
-            }
-        }
-        if (in3) {
-            const uint32_t a3 = pbase3[key];
-            if (pbase3[key + 1] != a3) {
-                G1XYZZ o = load_xyzz(in3 + a3);
-                xyzz_add_fn(run, o);
-            }
+        } else if (cy.in[0]) {  // empty in this piece: what the earlier pieces left (a walk that opens a bucket takes it along)
+            G1XYZZ o = carry_point(cy, key);
+            xyzz_add_fn(run, o);
         }
         xyzz_add_fn(tot, run);
     }
@@ -1982,14 +1990,29 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
     lim.dense_in = aff_rounds ? aff_entries[aff_rounds] : 0;
     KZG_CUDA(ctx, cudaMemcpyToSymbol(g_dbg, &lim, sizeof(lim)));
 #endif
+    // earlier pieces of the same MSM (add_in[0] the oldest): the walk opens every bucket with what they left, latest first
+    MsmCarry cy;
+    memset(&cy, 0, sizeof(cy));
+    if (n_add_in > 2) return set_err(ctx, KZG_ERR_ARG, "msm: at most two earlier pieces");
+    for (uint32_t k = 0; k < n_add_in; k++) {
+        if (add_in[k].nkeys != nkeys) return set_err(ctx, KZG_ERR_ARG, "msm: linked pieces must share the bucket geometry");
+        KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, add_in[k].ready, 0));
+        cy.in[n_add_in - 1 - k] = add_in[k].partials;
+        cy.pbase[n_add_in - 1 - k] = add_in[k].pbase;
+    }
     timed_begin(ctx, KZG_TIMED_MSM_ACCUMULATE);
-    if (aff_rounds)
-        KZG_LAUNCH(ctx, msm_accumulate_kernel<true>, ablocks, 128, 0, (const G1Affine*)nullptr, walk_x, walk_y,
-                   (const uint32_t*)nullptr, walk_offsets, segoff,
-                   nkeys, g.seg, partials);
+    if (aff_rounds && n_add_in)
+        KZG_LAUNCH(ctx, (msm_accumulate_kernel<true, true>), ablocks, 128, 0, (const G1Affine*)nullptr, walk_x, walk_y,
+                   (const uint32_t*)nullptr, walk_offsets, segoff, nkeys, g.seg, partials, cy);
+    else if (aff_rounds)
+        KZG_LAUNCH(ctx, (msm_accumulate_kernel<true, false>), ablocks, 128, 0, (const G1Affine*)nullptr, walk_x, walk_y,
+                   (const uint32_t*)nullptr, walk_offsets, segoff, nkeys, g.seg, partials, cy);
+    else if (n_add_in)
+        KZG_LAUNCH(ctx, (msm_accumulate_kernel<false, true>), ablocks, 128, 0, pts, (const Fq*)nullptr, (const Fq*)nullptr, sorted,
+                   offsets, segoff, nkeys, g.seg, partials, cy);
     else
-        KZG_LAUNCH(ctx, msm_accumulate_kernel<false>, ablocks, 128, 0, pts, (const Fq*)nullptr, (const Fq*)nullptr, sorted, offsets,
-                   segoff, nkeys, g.seg, partials);
+        KZG_LAUNCH(ctx, (msm_accumulate_kernel<false, false>), ablocks, 128, 0, pts, (const Fq*)nullptr, (const Fq*)nullptr, sorted,
+                   offsets, segoff, nkeys, g.seg, partials, cy);
     timed_end(ctx, KZG_TIMED_MSM_ACCUMULATE);
     timed_begin(ctx, KZG_TIMED_MSM_REDUCE);
     KZG_LAUNCH(ctx, msm_collapse_huge_kernel, 128, 512, 0, partials, segoff, huge + 1, huge);
@@ -2009,22 +2032,13 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
         KZG_CHECK_LAUNCH(ctx);
         return KZG_OK;
     }
-    const G1XYZZ* in_more[2] = {nullptr, nullptr};
-    const uint32_t* pbase_more[2] = {nullptr, nullptr};
-    if (n_add_in > 2) return set_err(ctx, KZG_ERR_ARG, "msm: at most two earlier pieces per reduction");
-    for (uint32_t k = 0; k < n_add_in; k++) {
-        if (add_in[k].nkeys != nkeys) return set_err(ctx, KZG_ERR_ARG, "msm: linked pieces must share the bucket geometry");
-        KZG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, add_in[k].ready, 0));
-        in_more[k] = add_in[k].partials;
-        pbase_more[k] = add_in[k].pbase;
-    }
     // table flavour: every bucket set IS a result (one per job); raw flavour: the sets are the windows of one result
     G1XYZZ* sums_out = g.table ? results : set_sums;
     {
         const dim3 grid((tg.n1 + RED_THREADS - 1) / RED_THREADS, g.nsets);
         // (measured: calling the shared addition at 126 registers / 16 warps per SM beats the inlined 168-register
         // version with its spills: 0.60 vs 0.66 ms for the whole reduction at 2^19 buckets)
-        KZG_LAUNCH(ctx, msm_reduce_level0_kernel, grid, RED_THREADS, 0, partials, segoff, in_more[0], pbase_more[0], in_more[1], pbase_more[1], g.nbuckets, 1u << tg.k0, u_arrays, tg.n1,
+        KZG_LAUNCH(ctx, msm_reduce_level0_kernel, grid, RED_THREADS, 0, partials, segoff, cy, g.nbuckets, 1u << tg.k0, u_arrays, tg.n1,
                    tvals);
     }
     {
@@ -2403,14 +2417,14 @@ static int srs_msm_host_pieces(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const
             cut[2] = n;
             // With two pieces the step is (upload of everything) + (MSM of the last 13/16): the last piece cannot start
             // before the whole upload has arrived (10 ms for 512 MiB), and the GPU idles once the first piece is done.
-            // Three linked pieces (1/16, 4/16, 11/16) keep it busy during the upload and leave a smaller rest: e2e 37.2 ->
-            // 36.3 ms at 2^24 points, 10.75 -> 10.33 at 2^22, no difference at 2^23 (20.3).  What remains above the
-            // resident-scalar MSM (32.8 ms) is the first upload (0.65 ms) and the pieces' own inefficiency: two more sorts,
-            // fewer affine rounds in the small pieces, one more addition per bucket and piece in the shared reduction.
+            // Three linked pieces (3/64, 13/64, 48/64) keep it busy during the upload and leave a smaller rest: e2e 37.2 ->
+            // 35.5 ms at 2^24 points, 20.7 -> 19.7 at 2^23, 10.75 -> 10.4 at 2^22.  What remains above the resident-scalar
+            // MSM (32.8 ms) is the first upload (0.5 ms) and the pieces' own inefficiency: two more sorts, fewer affine
+            // rounds in the small pieces.
             if (n >= (1ull << 22) && lanes && ctx->tuning.host_link) {
                 parts = 3;
-                cut[1] = n / 16;
-                cut[2] = n / 16 * 5;
+                cut[1] = n / 64 * 3;
+                cut[2] = n / 4;
             }
         }
         if (ctx->tuning.host_cut_a > 0) {  // tuning: cuts at a/64 and b/64 of n (b = 64: two pieces)
@@ -2447,12 +2461,13 @@ static int srs_msm_host_pieces(kzg_ctx* ctx, kzg_srs* srs, uint64_t first, const
             const MsmBases pb = srs_bases(ctx, srs, first + cut[k]);
             const MsmScalarSrc ps{tmp + cut[k], false};
             if (link) {
-                // every piece but the last stops after its fold; the last one reduces all of them.  The bucket sums of a
-                // piece live in its scratch arena until then: of three pieces the first and the last share lane 0 (one
-                // stream), so the first one works in the third arena.
+                // every piece but the last stops after its fold; a later piece opens each bucket of its walk with the sum
+                // the earlier ones left for it (MsmCarry) and the last one reduces.  The bucket sums of a piece live in
+                // its scratch arena until then: of three pieces the first and the last share lane 0 (one stream), so the
+                // first one works in the third arena.
                 const bool last = k + 1 == parts;
                 if (parts == 3 && k == 0) ctx->arena = 2;
-                r = msm_run_linked(ctx, pb, ps, cut[k + 1] - cut[k], slots, last ? lk : nullptr, last ? k : 0, last ? nullptr : &lk[k]);
+                r = msm_run_linked(ctx, pb, ps, cut[k + 1] - cut[k], slots, lk, k, last ? nullptr : &lk[k]);
                 ctx->arena = -1;
             } else {
                 r = msm_run(ctx, pb, ps, cut[k + 1] - cut[k], slots + k);
