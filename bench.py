@@ -356,12 +356,13 @@ def run_b200(args):
     algorithmic = macs_per_launch / (phase_ms * 1e-3) if phase_ms > 0 else 0.0
     # EXECUTED work: wide MACs the kernels really issue.  Counted by ncu (fmaheavy-pipe thread instructions of these
     # kernels at this size, profiles/traffic.json, valid while the kernel sources hash the same); else modelled: an entry
-    # absorbed by an affine round ~6.3 products (3 for its share of the inversion incl. the recursive levels, 3 for the
-    # chord formulas), an entry left to the walk 10, 128 wide MACs per product.
+    # absorbed by an affine round 778 wide MACs (forward product 128, backward 4 x 128 + one squaring of 100, ~0.3 products
+    # for its share of the recursive inversion), an entry left to the walk 1160 (6 products, 2 squarings, R (Q - X3) -
+    # Y1 PPP as two products under one reduction = 192).
     counted = ncu_counted("msm_accumulation_2_%d" % args.log_n, "msm") if world == 1 else None
     entries = float(shard) * geom["windows"]
     left = entries / (1 << geom["affine_rounds"])
-    modelled_macs = (left * 10 + (entries - left) * 6.3) * 128
+    modelled_macs = left * 1160.0 + (entries - left) * 778.0
     executed_macs = counted["fmaheavy_thread_instructions"] if counted else modelled_macs
     executed = executed_macs / (phase_ms * 1e-3) if phase_ms > 0 else 0.0
     peaks, peak_kind = measured_peaks()
@@ -372,7 +373,7 @@ def run_b200(args):
                    "msm_aff_backward_kernel) + msm_accumulate_kernel" % geom["affine_rounds"]) if affine else "msm_accumulate_kernel",
         # frac = EXECUTED wide MACs / kernel time / measured pipe peak: a utilisation figure (<= 1)
         "achieved": executed / 1e12, "peak": peak / 1e12, "unit": "Tmac/s", "frac": executed / peak if peak else None,
-        "executed_macs_source": "ncu (profiles/traffic.json)" if counted else "model (6.3 / 10 products per entry)",
+        "executed_macs_source": "ncu (profiles/traffic.json)" if counted else "model (778 / 1160 wide MACs per entry)",
         "traffic": counted["dram_bytes"] if counted else None,
         "algorithmic_bytes": 64.0 * entries,
         # the SURVEY 8d unit (21 760 MACs per point whatever the kernel really does): > 1 means algorithmic savings
