@@ -16,8 +16,9 @@ struct MsmTuning {
     int aff_rounds = -1;            // batched-affine rounds before the XYZZ walk; -1: the cost rule of msm_affine_rounds
     uint32_t aff_m = 16;            // output points per thread of a round
     int aff_chunks = 0;             // chunks a round is launched in (inversion hidden under the other chunks); 0: auto
-    uint64_t aff_min_entries = 20ull << 20;  // no rounds below this many bucket entries
-    uint64_t aff_min_left = 13ull << 19;     // a round must leave at least this many points (6.8 M: measured, r02_msm_rounds.md)
+    uint64_t aff_min_entries = 40ull << 20;  // no rounds below this many bucket entries (refit after the walk got 8 % cheaper:
+    uint64_t aff_min_left = 12000000;        // 0 rounds at 2^21 points, 2 at 2^22, 3 at 2^23, 4 at 2^24 -- r02_msm_rounds.md);
+                                             // a round must leave at least this many points
     double aff_min_fill = 6.0;      // ... and find at least this many entries per bucket
     int part_sort = -1;             // 0 / 1: direct counting sort / two-level partition sort; -1: by size
     int red_k0 = -1;                // log2 of the level-0 radix of the bucket reduction; -1: by size

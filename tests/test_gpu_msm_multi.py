@@ -261,3 +261,37 @@ def test_host_scalar_pieces_share_one_reduction(curve, tau, log_n, table_c, cuts
         curve.set_option("host_cut_a", -1)
         curve.set_option("host_cut_b", -1)
         curve.lib.kzg_srs_free(curve.ctx, srs)
+
+
+@pytest.mark.parametrize("rounds", [1, 3])
+def test_linked_pieces_with_affine_rounds(curve, tau, rounds):
+    """three linked pieces whose walks run over the dense lists the batched-affine rounds leave (msm_accumulate_kernel
+    <DIRECT, CARRY>: at the library's own sizes only pieces of 2^24-point MSMs get there): forced rounds, cuts at 8 / 64 and
+    24 / 64, uniform and skewed scalars -- the same point as the resident-scalar MSM without rounds"""
+    import torch
+    from kzg_grandsums_study_b200 import synthetic
+    from kzg_grandsums_study_b200._lib import as_ptr
+    lib, ctx = curve.lib, curve.ctx
+    n = 1 << 21
+    srs = _srs(curve, tau, n, 12)
+    try:
+        scal = synthetic.random_fr_std(77 + rounds, n)
+        skew = scal.copy()
+        skew[n // 8: n // 4] = 0                # the middle piece starts with nothing
+        skew[n // 2:, 1:] = 0                   # 64-bit scalars: most buckets empty in the last piece
+        for data in (scal, skew):
+            host = torch.from_numpy(data.view(np.uint8).reshape(-1).copy()).pin_memory()
+            dev = curve.to_device(data.tobytes())
+            want = bytearray(64)
+            curve.set_option("aff_rounds", 0)
+            curve.check(lib.kzg_srs_msm(ctx, srs, 0, dev.handle, n, as_ptr(want)))
+            curve.set_option("aff_rounds", rounds)
+            curve.set_option("host_cut_a", 8)
+            curve.set_option("host_cut_b", 24)
+            got = bytearray(64)
+            curve.check(lib.kzg_srs_msm_host(ctx, srs, 0, as_ptr(host), n, as_ptr(got)))
+            assert bytes(got) == bytes(want), rounds
+    finally:
+        for k in ("aff_rounds", "host_cut_a", "host_cut_b"):
+            curve.set_option(k, -1)
+        curve.lib.kzg_srs_free(curve.ctx, srs)
