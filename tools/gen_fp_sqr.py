@@ -260,7 +260,7 @@ def emulate(blocks, aval, p):
     return t
 
 
-def check():
+def check(n_random=20000, n_extreme=2000):
     blocks = build()
     n_wide = 0
     n_other = 0
@@ -276,9 +276,9 @@ def check():
         rinv = pow(1 << 256, -1, p)
         cases = [0, 1, 2, p - 1, p - 2, (1 << 253) - 1, (1 << 224) - 1, M32, p >> 1]
         cases += [sum(M32 << (32 * i) for i in range(8)) % p]
-        cases += [rng.randrange(p) for _ in range(20000)]
+        cases += [rng.randrange(p) for _ in range(n_random)]
         # operands with extreme limbs: all-ones limbs force every carry
-        for _ in range(2000):
+        for _ in range(n_extreme):
             a = 0
             for i in range(8):
                 a |= rng.choice((0, M32, 1, 0x80000000, rng.randrange(1 << 32))) << (32 * i)
@@ -542,7 +542,7 @@ def emulate_named(blocks, vals, p):
     return sum(v["t%d" % j] << (32 * j) for j in range(8))
 
 
-def check_mul2():
+def check_mul2(n_random=20000, n_extreme=4000):
     blocks = build_mul2()
     rng = random.Random(11)
     worst = 0
@@ -550,8 +550,8 @@ def check_mul2():
         rinv = pow(1 << 256, -1, p)
         edge = [0, 1, p - 1, p - 2, (1 << 253) - 1, p >> 1, M32, sum(M32 << (32 * i) for i in range(8)) % p]
         cases = [(a_, b_, c_, d_) for a_ in edge for b_ in edge for c_ in edge for d_ in edge]
-        cases += [tuple(rng.randrange(p) for _ in range(4)) for _ in range(20000)]
-        for _ in range(4000):
+        cases += [tuple(rng.randrange(p) for _ in range(4)) for _ in range(n_random)]
+        for _ in range(n_extreme):
             ops = []
             for _k in range(4):
                 a_ = 0
@@ -669,7 +669,7 @@ def build_mulk():
     return blocks
 
 
-def check_mulk():
+def check_mulk(n_random=20000, n_extreme=6000):
     blocks = build_mulk()
     n_wide = sum(1 for b in blocks for t in b.ins
                  if t[0].startswith(("mad", "mul")) and not (isinstance(t[3], tuple) and t[3][0] == "inv"))
@@ -682,8 +682,8 @@ def check_mulk():
         edge = [0, 1, p - 1, p - 2, (1 << 253) - 1, p >> 1, M32, (1 << 128) - 1, ((1 << 128) - 1) << 128 & ((1 << 253) - 1),
                 sum(M32 << (32 * i) for i in range(8)) % p, (1 << 128), (1 << 127) | (1 << 253) % p]
         cases = [(x_, y_) for x_ in edge for y_ in edge]
-        cases += [(rng.randrange(p), rng.randrange(p)) for _ in range(20000)]
-        for _ in range(6000):
+        cases += [(rng.randrange(p), rng.randrange(p)) for _ in range(n_random)]
+        for _ in range(n_extreme):
             ops = []
             for _k in range(2):
                 a_ = 0
