@@ -14,7 +14,7 @@
 // tests/).  None of them changes a result -- every path ends in the same canonical affine point.
 struct MsmTuning {
     int aff_rounds = -1;            // batched-affine rounds before the XYZZ walk; -1: the cost rule of msm_affine_rounds
-    uint32_t aff_m = 16;            // output points per thread of a round
+    uint32_t aff_m = 32;            // output points per thread of a round (measured 8 / 12 / 16 / 24 / 32: 26.1 / 25.6 / 25.2 / 25.1 / 25.0 ms for the rounds at 2^24 points)
     int aff_chunks = 0;             // chunks a round is launched in (inversion hidden under the other chunks); 0: auto
     uint64_t aff_min_entries = 40ull << 20;  // no rounds below this many bucket entries (refit after the walk got 8 % cheaper:
     uint64_t aff_min_left = 12000000;        // 0 rounds at 2^21 points, 2 at 2^22, 3 at 2^23, 4 at 2^24 -- r02_msm_rounds.md);
