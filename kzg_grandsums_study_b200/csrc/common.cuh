@@ -16,14 +16,15 @@ struct MsmTuning {
     int aff_rounds = -1;            // batched-affine rounds before the XYZZ walk; -1: the cost rule of msm_affine_rounds
     uint32_t aff_m = 32;            // output points per thread of a round (measured 8 / 12 / 16 / 24 / 32: 26.1 / 25.6 / 25.2 / 25.1 / 25.0 ms for the rounds at 2^24 points)
     int aff_chunks = 0;             // chunks a round is launched in (inversion hidden under the other chunks); 0: auto
-    uint64_t aff_min_entries = 40ull << 20;  // no rounds below this many bucket entries (refit after the walk got 8 % cheaper:
-    uint64_t aff_min_left = 12000000;        // 0 rounds at 2^21 points, 2 at 2^22, 3 at 2^23, 4 at 2^24 -- r02_msm_rounds.md);
-                                             // a round must leave at least this many points
+    uint64_t aff_min_entries = 20ull << 20;  // no rounds below this many bucket entries
+    uint64_t aff_min_left = 13ull << 19;     // a round must leave at least this many points (6.8 M: 2 rounds at 2^21 points, 3 at
+                                             // 2^22 / 2^23, 4 at 2^24 -- the sweeps of r02_msm_rounds.md)
     double aff_min_fill = 6.0;      // ... and find at least this many entries per bucket
     int part_sort = -1;             // 0 / 1: direct counting sort / two-level partition sort; -1: by size
     int red_k0 = -1;                // log2 of the level-0 radix of the bucket reduction; -1: by size
     int tail_width = 0;             // threads per tail task (32 / 64 / 128); 0: by size
     int host_cut_a = 0, host_cut_b = 64;  // host-scalar MSM: piece cuts at a/64 and b/64 of the points; 0: default
+    int aff_interleave = 2;         // outputs of a round dealt to the lanes of a warp one by one (2: every round, 1: dense rounds only, 0: m consecutive outputs per thread)
     int host_link = 1;              // the pieces of a host-scalar MSM over a window table share one bucket reduction (0: one each)
     uint32_t host_piece_min_log = 21;     // ... pieces from 2^this points on (2^21: the 8-GPU shard, 8.3 -> 7.5 ms e2e)
     int split_min_log = -1, split_max_log = -1;  // two-lane split of ONE msm (off: measured slower since the affine rounds)

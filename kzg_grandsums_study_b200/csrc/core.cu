@@ -28,6 +28,7 @@ int ctx_set_option(kzg_ctx* ctx, const char* name, long long value) {
     else if (k == "tail_width") t.tail_width = reset ? def.tail_width : (int)value;
     else if (k == "host_cut_a") t.host_cut_a = reset ? def.host_cut_a : (int)value;
     else if (k == "host_cut_b") t.host_cut_b = reset ? def.host_cut_b : (int)value;
+    else if (k == "aff_interleave") t.aff_interleave = reset ? def.aff_interleave : (int)value;
     else if (k == "host_link") t.host_link = reset ? def.host_link : (int)value;
     else if (k == "host_piece_min_log") t.host_piece_min_log = reset ? def.host_piece_min_log : (uint32_t)value;
     else if (k == "split_min_log") t.split_min_log = reset ? def.split_min_log : (int)value;
@@ -319,7 +320,7 @@ int kzg_ctx_create(int device, void* stream, kzg_ctx** out) {
     ctx->no_split = getenv("KZGB200_NO_SPLIT") != nullptr;
     // the tuning knobs, read once (kzg_ctx_set_option changes them later)
     static const char* const knobs[] = {"aff_rounds", "aff_m", "aff_chunks", "aff_min_entries_log", "aff_min_left_log",
-                                        "aff_min_fill", "part_sort", "red_k0", "tail_width", "host_piece_min_log", "host_link",
+                                        "aff_min_fill", "part_sort", "red_k0", "tail_width", "host_piece_min_log", "host_link", "aff_interleave",
                                         "split_min_log", "split_max_log", "msm_merge", "timeline", "ntt_tile", "ntt_big_table"};
     for (const char* k : knobs) {
         std::string env = "KZGB200_";

@@ -870,7 +870,6 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_kernel(const G1Affine* 
 // Exceptional pairs are decided from the operands alone, identically in both kernels: an operand at infinity, P + P
 // (tangent: d = 2 y, numerator 3 x^2), P + (-P) = infinity; they put d = 1 into the batch where no quotient is needed.
 // ---------------------------------------------------------------------------------------------
-constexpr int AFF_M = 16;
 constexpr int AFF_THREADS = 128;
 struct AffRound {
     const G1Affine* bases;    // round 1: window table / points, addressed through `sorted` (index | sign << 31)
@@ -987,26 +986,40 @@ __device__ __forceinline__ Fq aff_load_x(const AffRound& a, uint32_t h) {
     return INDEXED ? load_fq_gather(&(a.bases + (h & 0x7fffffffu))->x) : load_fq_ldg(a.in_x + h);
 }
 
+// Outputs of thread t: `count` of them, first, first + step, ...  Plain: m consecutive outputs.  Interleaved (il): the 32
+// lanes of a warp share a tile of 32 m consecutive outputs, lane l takes l, l + 32, ... -- at every step a warp then reads
+// 32 CONSECUTIVE pairs of the dense list and writes 32 consecutive results (coalesced) instead of 32 runs 2 m points apart.
+__device__ __forceinline__ void aff_thread_outputs(uint32_t t, uint32_t m, uint32_t total, bool il, uint32_t& first,
+                                                   uint32_t& count, uint32_t& step) {
+    const uint64_t f = il ? (uint64_t)(t >> 5) * 32 * m + (t & 31) : (uint64_t)t * m;
+    step = il ? 32u : 1u;
+    first = (uint32_t)f;
+    count = 0;
+    if (f < total) {
+        const uint64_t left = (total - f + step - 1) / step;
+        count = (uint32_t)(left < m ? left : m);
+    }
+}
+
 // `desc`: the operand handles of every output, desc[j][t] = (h1, h2), h2 == h1 when the output has a single operand
 // (handles of one bucket are distinct: an entry is one (window, point) pair) -- the backward pass then needs no bucket
 // cursor of its own and its gathers are ONE load away from their addresses instead of three (offsets -> sorted[] -> table).
 template <bool INDEXED>
 __global__ void __launch_bounds__(AFF_THREADS, 6) msm_aff_forward_kernel(AffRound a, uint32_t m, uint32_t t_first, uint32_t t_end,
                                                                          Fq* __restrict__ prefix, Fq* __restrict__ totals,
-                                                                         uint2* __restrict__ desc) {
+                                                                         uint2* __restrict__ desc, bool il) {
     const uint32_t t = t_first + blockIdx.x * blockDim.x + threadIdx.x;  // (a round is launched in chunks of threads)
     if (t >= t_end) return;
     Fq acc = fp_one<FqP>();
     const uint32_t total = a.off_out[a.nkeys];
-    const uint64_t begin64 = (uint64_t)t * m;
-    if (begin64 < total) {
-        const uint32_t begin = (uint32_t)begin64;
-        const uint32_t end = (uint32_t)min((uint64_t)total, begin64 + m);
-        AffCursor c = aff_seek(a, begin);
+    uint32_t first, count, step;
+    aff_thread_outputs(t, m, total, il, first, count, step);
+    if (count) {
+        AffCursor c = aff_seek(a, first);
         uint32_t h1, h2;
         bool pair;
         Fq x1, x2;  // x coordinates of the pair in hand, fetched one iteration ahead
-        aff_handles<INDEXED>(a, c, begin, h1, h2, pair);
+        aff_handles<INDEXED>(a, c, first, h1, h2, pair);
         if (pair) {
             x1 = aff_load_x<INDEXED>(a, h1);
             x2 = aff_load_x<INDEXED>(a, h2);
@@ -1014,22 +1027,22 @@ __global__ void __launch_bounds__(AFF_THREADS, 6) msm_aff_forward_kernel(AffRoun
         Fq* pre = prefix + t;
         uint2* dsc = desc + t;
 #pragma unroll 1
-        for (uint32_t o = begin; o < end; o++, pre += a.nthreads) {
-            if (KZG_IDX_OK((uint64_t)(o - begin) * a.nthreads + t, KZG_DBG(prefix_elems), DBG_FWD_PREFIX))
+        for (uint32_t j = 0, o = first; j < count; j++, o += step, pre += a.nthreads) {
+            if (KZG_IDX_OK((uint64_t)j * a.nthreads + t, KZG_DBG(prefix_elems), DBG_FWD_PREFIX))
                 *dsc = make_uint2(h1, pair ? h2 : h1);
             dsc += a.nthreads;
             uint32_t nh1 = 0, nh2 = 0;
             bool npair = false;
             Fq nx1, nx2;
-            if (o + 1 < end) {
-                aff_step_up(a, c, o + 1);
-                aff_handles<INDEXED>(a, c, o + 1, nh1, nh2, npair);
+            if (j + 1 < count) {
+                aff_step_up(a, c, o + step);
+                aff_handles<INDEXED>(a, c, o + step, nh1, nh2, npair);
                 if (npair) {
                     nx1 = aff_load_x<INDEXED>(a, nh1);
                     nx2 = aff_load_x<INDEXED>(a, nh2);
                 }
             }
-            if (pair && KZG_IDX_OK((uint64_t)(o - begin) * a.nthreads + t, KZG_DBG(prefix_elems), DBG_FWD_PREFIX)) {
+            if (pair && KZG_IDX_OK((uint64_t)j * a.nthreads + t, KZG_DBG(prefix_elems), DBG_FWD_PREFIX)) {
                 Fq d;
                 if (fp_eq(x1, x2) || fp_is_zero(x1) || fp_is_zero(x2)) {  // exceptional: decide on the full points
                     const G1Affine p1 = aff_load_point<INDEXED>(a, h1), p2 = aff_load_point<INDEXED>(a, h2);
@@ -1061,38 +1074,37 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRou
                                                                                const Fq* __restrict__ prefix,
                                                                                const Fq* __restrict__ inv_totals,
                                                                                const uint2* __restrict__ desc,
-                                                                               Fq* __restrict__ out_x, Fq* __restrict__ out_y) {
+                                                                               Fq* __restrict__ out_x, Fq* __restrict__ out_y, bool il) {
     const uint32_t t = t_first + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t_end) return;
     const uint32_t total = a.off_out[a.nkeys];
-    const uint64_t begin64 = (uint64_t)t * m;
-    if (begin64 >= total) return;
-    const uint32_t begin = (uint32_t)begin64;
-    const uint32_t end = (uint32_t)min((uint64_t)total, begin64 + m);
+    uint32_t first, count, step;
+    aff_thread_outputs(t, m, total, il, first, count, step);
+    if (count == 0) return;
     Fq s = load_fq_ldg(inv_totals + t);
-    const uint64_t top = (uint64_t)(end - 1 - begin) * a.nthreads + t;
+    const uint64_t top = (uint64_t)(count - 1) * a.nthreads + t;
     const Fq* pre_ptr = prefix + top;
     const uint2* dsc = desc + top;
-    uint2 h = __ldg(dsc);                                                  // output o
-    uint2 hn = end - 1 > begin ? __ldg(dsc - a.nthreads) : make_uint2(0u, 0u);  // output o - 1
+    uint2 h = __ldg(dsc);                                                  // output j
+    uint2 hn = count > 1 ? __ldg(dsc - a.nthreads) : make_uint2(0u, 0u);   // output j - 1
     G1Affine p1, p2;
     Fq pre;
     if (h.y != h.x) {
-        aff_request_pair<INDEXED>(a, end - 1, h.x, h.y, p1, p2);
+        aff_request_pair<INDEXED>(a, 0, h.x, h.y, p1, p2);
         pre = load_fq_ldg(pre_ptr);
     } else {
         p1 = aff_request_point<INDEXED>(a, h.x);
     }
 #pragma unroll 1
-    for (uint32_t o = end - 1;; o--, pre_ptr -= a.nthreads, dsc -= a.nthreads) {
-        const bool more = o > begin;
+    for (uint32_t j = count - 1, o = first + (count - 1) * step;; j--, o -= step, pre_ptr -= a.nthreads, dsc -= a.nthreads) {
+        const bool more = j > 0;
         G1Affine n1, n2;
         Fq npre;
         uint2 hnn = make_uint2(0u, 0u);
         if (more) {
-            if (o - 1 > begin) hnn = __ldg(dsc - 2 * (size_t)a.nthreads);   // output o - 2
+            if (j > 1) hnn = __ldg(dsc - 2 * (size_t)a.nthreads);   // output j - 2
             if (hn.y != hn.x) {
-                aff_request_pair<INDEXED>(a, o - 1, hn.x, hn.y, n1, n2);
+                aff_request_pair<INDEXED>(a, 0, hn.x, hn.y, n1, n2);
                 npre = load_fq_ldg(pre_ptr - a.nthreads);
             } else {
                 n1 = aff_request_point<INDEXED>(a, hn.x);
@@ -1732,7 +1744,8 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
     // batched-affine rounds: two point lists (ping-pong), prefix products, thread products
     size_t o_aff_pts[2] = {0, 0}, o_aff_prefix = 0, o_aff_totals = 0, o_aff_desc = 0;
     if (aff_rounds) {
-        const uint64_t threads1 = (aff_entries[1] + aff_m - 1) / aff_m;
+        // (whole warps: with interleaved outputs the 32 lanes of a warp share one tile of 32 m outputs)
+        const uint64_t threads1 = ((aff_entries[1] + aff_m - 1) / aff_m + 31) / 32 * 32;
         o_aff_pts[0] = off;   off = align_up(off + sizeof(G1Affine) * aff_entries[1], 256);
         o_aff_pts[1] = off;   off = align_up(off + sizeof(G1Affine) * (aff_rounds > 1 ? aff_entries[2] : 0), 256);
         o_aff_prefix = off;   off = align_up(off + sizeof(Fq) * threads1 * aff_m, 256);
@@ -1806,8 +1819,8 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
         lim.sorted_entries = max_entries;
         lim.mid_entries = max_entries;
         lim.partials = max_parts;
-        lim.prefix_elems = aff_rounds ? ((aff_entries[1] + aff_m - 1) / aff_m) * aff_m : 0;
-        lim.totals = aff_rounds ? (aff_entries[1] + aff_m - 1) / aff_m : 0;
+        lim.prefix_elems = aff_rounds ? (((aff_entries[1] + aff_m - 1) / aff_m + 31) / 32 * 32) * aff_m : 0;
+        lim.totals = aff_rounds ? ((aff_entries[1] + aff_m - 1) / aff_m + 31) / 32 * 32 : 0;
         lim.table_points = bases.table ? (uint64_t)(g.nwin - 1) * g.stride + n : n;
         lim.nkeys = nkeys;
         const unsigned int zero = 0;
@@ -1868,6 +1881,7 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
         Fq* prefix = (Fq*)(sc + o_aff_prefix);
         Fq* totals = (Fq*)(sc + o_aff_totals);
         uint2* desc = (uint2*)(sc + o_aff_desc);
+        const bool aff_il = tn.aff_interleave == 2 || (tn.aff_interleave == 1 && r > 1);
         AffRound ar;
         ar.bases = pts;
         ar.sorted = r == 1 ? sorted : nullptr;
@@ -1876,7 +1890,7 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
         ar.off_in = walk_offsets;
         ar.off_out = off_out;
         ar.nkeys = nkeys;
-        ar.nthreads = (uint32_t)((aff_entries[r] + aff_m - 1) / aff_m);
+        ar.nthreads = (uint32_t)(((aff_entries[r] + aff_m - 1) / aff_m + 31) / 32 * 32);
 #ifdef KZG_BOUNDS_CHECK
         KZG_CUDA(ctx, cudaDeviceSynchronize());
         lim.aff_cap[0] = aff_entries[r];                       // what this round may write
@@ -1917,9 +1931,9 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
             const uint32_t blocks = (t1 - t0 + AFF_THREADS - 1) / AFF_THREADS;
             ctx->stream = (k & 1) ? side_stream : main_stream;
             if (r == 1)
-                KZG_LAUNCH(ctx, msm_aff_forward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, desc);
+                KZG_LAUNCH(ctx, msm_aff_forward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, desc, aff_il);
             else
-                KZG_LAUNCH(ctx, msm_aff_forward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, desc);
+                KZG_LAUNCH(ctx, msm_aff_forward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, desc, aff_il);
             mark(ctx->stream, "F_end", k);
             if (piped) {
                 cudaEvent_t fwd_done = order_event(ctx);
@@ -1948,9 +1962,9 @@ int msm_run_multi(kzg_ctx* ctx, const MsmBases& bases, const MsmJobs& jobs, G1XY
             if (rr != KZG_OK) continue;
             mark(ctx->stream, "B_begin", k);
             if (r == 1)
-                KZG_LAUNCH(ctx, msm_aff_backward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, desc, out_x, out_y);
+                KZG_LAUNCH(ctx, msm_aff_backward_kernel<true>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, desc, out_x, out_y, aff_il);
             else
-                KZG_LAUNCH(ctx, msm_aff_backward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, desc, out_x, out_y);
+                KZG_LAUNCH(ctx, msm_aff_backward_kernel<false>, blocks, AFF_THREADS, 0, ar, aff_m, t0, t1, prefix, totals, desc, out_x, out_y, aff_il);
             mark(ctx->stream, "B_end", k);
         }
         ctx->stream = main_stream;
