@@ -15,4 +15,4 @@ python $S multi gpurun_out/r02_msm21_launches.csv profiles/r02_msm21_launches.md
   "round 2 — every launch of one 2^21-point SRS MSM (the 8-GPU shard: table c = 20, 2 batched-affine rounds)" msm_part_hist
 python $S multi gpurun_out/r02_ntt24_launches.csv profiles/r02_ntt24_launches.md \
   "round 2 — the passes of a 2^24 NTT (forward, then inverse)" ntt_strided
-python $S launches gpurun_out/r02_prove20_launches.csv profiles/r02_prove20_launches.md "round 2 — launch list of one grand-sum proof at n = 2^20" 229
+python $S launches gpurun_out/r02_prove20_launches.csv profiles/r02_prove20_launches.md "round 2 — launch list of one grand-sum proof at n = 2^20" 203
