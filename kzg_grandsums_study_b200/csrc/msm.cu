@@ -15,13 +15,14 @@
 //                         polynomial: Fr.batchFromMontgomery fused), histogram of bucket keys (L2 atomics)
 //   2. msm_scan_*         exclusive prefix sums of bucket sizes, then of partial-sum slots per bucket (2 x 3 launches)
 //   3. msm_digits<scatter> counting-sort scatter of (point index | sign) into bucket order
-//   3b. msm_aff_forward / fq_batch_inverse / msm_aff_backward   (from 2^22 points on) batched-affine rounds: the entries
-//                         of every bucket are added pairwise with one shared inversion per round (~6.3 modmul per
+//   3b. msm_aff_forward / fq_batch_inverse / msm_aff_backward   (from 2^21 points on) batched-affine rounds: the entries
+//                         of every bucket are added pairwise with one shared inversion per round (~780 wide MACs per
 //                         addition), the list halves each time and ends as a dense array of affine points
 //   4. msm_accumulate     one thread per fixed-length SLICE of the sorted list (equal work per lane whatever the
 //                         bucket sizes): XYZZ += affine, parking a partial sum at every bucket boundary; random 64 B
 //                         gathers (or the dense list the rounds left), next point prefetched during the add.
-//                         THE IMAD-bound kernel: 10 modmul (1360 limb MACs) per entry.
+//                         THE IMAD-bound kernel: 1160 wide MACs per entry (6 products, 2 squarings, 1 double product).
+//                         A later piece of a host-scalar MSM opens its buckets with the earlier pieces' sums (MsmCarry).
 //   5. msm_collapse       buckets spread over many slices: block-parallel sum of their partials
 //   6. msm_reduce_level0  sum_b (b+1) S_b: chunks of 4-8 consecutive buckets -> plain sum U_q and weighted partial t_q
 //                         (running-sum trick, the only pass over all buckets)
