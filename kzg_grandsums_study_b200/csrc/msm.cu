@@ -719,12 +719,29 @@ __device__ __forceinline__ uint4 ldg_gather16(const void* p) {
     asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// A coordinate is ONE 256-bit access (sm_100: LDG.E.256 / STG.E.256), not two 128-bit ones: half the instructions in the
+// load / store queues of the accumulation kernels (ncu --set full of the backward pass: lg_throttle 0.7-0.8 stalls per
+// issue with 128-bit accesses).  Every Fq these helpers touch sits at a multiple of 32 bytes: the table, the dense lists,
+// the prefix / total arrays are 256-byte-aligned arrays of 32- or 64-byte elements.  (The XYZZ partial sums stay on
+// 128-bit accesses: ptxas 12.9 crashes on 256-bit accesses inside the shared group-law functions.)
 __device__ __forceinline__ Fq load_fq_gather(const Fq* p) {
     Fq r;
-    const uint4 a = ldg_gather16(p), b = ldg_gather16(reinterpret_cast<const uint4*>(p) + 1);
-    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    asm volatile("ld.global.nc.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+                 : "l"(p));
     return r;
+}
+__device__ __forceinline__ Fq load_fq_global(const Fq* p) {  // read-only data, streamed
+    Fq r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void store_fq_global(Fq* p, const Fq& v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.l[0]), "r"(v.l[1]), "r"(v.l[2]), "r"(v.l[3]),
+                 "r"(v.l[4]), "r"(v.l[5]), "r"(v.l[6]), "r"(v.l[7])
+                 : "memory");
 }
 __device__ __forceinline__ G1Affine load_affine_gather(const G1Affine* p) {
     G1Affine r;
@@ -734,12 +751,8 @@ __device__ __forceinline__ G1Affine load_affine_gather(const G1Affine* p) {
 }
 __device__ __forceinline__ G1Affine load_affine(const G1Affine* p) {
     G1Affine r;
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-    r.x.l[0] = a.x; r.x.l[1] = a.y; r.x.l[2] = a.z; r.x.l[3] = a.w;
-    r.x.l[4] = b.x; r.x.l[5] = b.y; r.x.l[6] = b.z; r.x.l[7] = b.w;
-    r.y.l[0] = c.x; r.y.l[1] = c.y; r.y.l[2] = c.z; r.y.l[3] = c.w;
-    r.y.l[4] = d.x; r.y.l[5] = d.y; r.y.l[6] = d.z; r.y.l[7] = d.w;
+    r.x = load_fq_global(&p->x);
+    r.y = load_fq_global(&p->y);
     return r;
 }
 __device__ __forceinline__ void store_xyzz(G1XYZZ* p, const G1XYZZ& v) {
@@ -779,13 +792,8 @@ __device__ __noinline__ G1XYZZ carry_point(const MsmCarry& cy, uint32_t key) {
 
 __device__ __forceinline__ G1Affine load_dense_point(const Fq* xs, const Fq* ys, uint32_t i) {
     G1Affine r;
-    const uint4* qx = reinterpret_cast<const uint4*>(xs + i);
-    const uint4* qy = reinterpret_cast<const uint4*>(ys + i);
-    uint4 a = __ldg(qx), b = __ldg(qx + 1), c = __ldg(qy), d = __ldg(qy + 1);
-    r.x.l[0] = a.x; r.x.l[1] = a.y; r.x.l[2] = a.z; r.x.l[3] = a.w;
-    r.x.l[4] = b.x; r.x.l[5] = b.y; r.x.l[6] = b.z; r.x.l[7] = b.w;
-    r.y.l[0] = c.x; r.y.l[1] = c.y; r.y.l[2] = c.z; r.y.l[3] = c.w;
-    r.y.l[4] = d.x; r.y.l[5] = d.y; r.y.l[6] = d.z; r.y.l[7] = d.w;
+    r.x = load_fq_global(xs + i);
+    r.y = load_fq_global(ys + i);
     return r;
 }
 
@@ -884,14 +892,7 @@ struct AffRound {
 };
 enum { AFF_ADD = 0, AFF_TAKE_1 = 1, AFF_TAKE_2 = 2, AFF_DOUBLE = 3, AFF_INF = 4 };
 
-__device__ __forceinline__ Fq load_fq_ldg(const Fq* p) {
-    Fq r;
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1);
-    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-    return r;
-}
+__device__ __forceinline__ Fq load_fq_ldg(const Fq* p) { return load_fq_global(p); }
 // operand handles: position in the dense input list, or (round 1) the sorted entry itself: index | sign << 31
 // (the sign is applied by the consumer: a prefetch must not touch what it loads -- the first use of a loaded
 // register is where the warp waits)
@@ -1051,7 +1052,7 @@ __global__ void __launch_bounds__(AFF_THREADS, 6) msm_aff_forward_kernel(AffRoun
                 } else {
                     d = fp_sub(x2, x1);
                 }
-                fp_store(pre, acc);
+                store_fq_global(pre, acc);
                 acc = fp_mul(acc, d);
             }
             h1 = nh1;
@@ -1061,7 +1062,7 @@ __global__ void __launch_bounds__(AFF_THREADS, 6) msm_aff_forward_kernel(AffRoun
             x2 = nx2;
         }
     }
-    if (KZG_IDX_OK(t, KZG_DBG(totals), DBG_FWD_TOTALS)) fp_store(totals + t, acc);
+    if (KZG_IDX_OK(t, KZG_DBG(totals), DBG_FWD_TOTALS)) store_fq_global(totals + t, acc);
 }
 
 // Backward pass, driven by the forward pass's descriptors: no bucket cursor of its own (measured against a version that
@@ -1137,8 +1138,8 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) msm_aff_backward_kernel(AffRou
             }
         }
         if (KZG_IDX_OK(o, KZG_DBG(aff_cap[0]), DBG_BWD_OUT)) {
-            fp_store(out_x + o, r.x);
-            fp_store(out_y + o, r.y);
+            store_fq_global(out_x + o, r.x);
+            store_fq_global(out_y + o, r.y);
         }
         if (!more) break;
         p1 = n1;
