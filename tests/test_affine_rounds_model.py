@@ -7,6 +7,8 @@ for the pairs that need no quotient (operand at infinity, P + (-P)) and d = 2y f
 contract -- same classification, same formulas -- and the test checks what the CUDA path relies on: the per-bucket sums
 are unchanged, a bucket of k entries holds ceil(k / 2^r) points after r rounds, and the result of the MSM
 (G1.multiExpAffine, reference src/polynomial/polynomial.js:1112) is the same whatever the number of rounds.
+The second half models the linked pieces of a host-scalar MSM (MsmReduceLink / MsmCarry: a later piece opens its buckets
+with what the earlier ones left, empty buckets are picked up by the reduction) the same way.
 """
 import random
 
@@ -124,3 +126,82 @@ def test_msm_result_does_not_depend_on_the_rounds():
         for b, lst in enumerate(cur):
             acc = bn.g1_add(acc, bn.g1_mul(_sum(lst), b + 1))
         assert acc == want, rounds
+
+
+# ---- linked pieces of a host-scalar MSM (csrc/msm.cu: MsmReduceLink / MsmCarry) ---------------------------------------
+# kzg_srs_msm_host cuts the scalars into pieces whose uploads hide behind compute.  Over the window table all pieces share
+# ONE bucket geometry; every piece but the last stops after folding its bucket sums -- one point per NON-EMPTY bucket,
+# nothing for an empty one -- and a later piece opens every bucket of its walk with the sum the LATEST earlier piece that
+# touched the bucket left for it (which already contains the pieces before that one).  Buckets that are empty in the last
+# piece are picked up by the reduction the same way.  The model states that contract.
+def _digit_buckets(bases, scalars, first, c, nwin):
+    """entries of the points first .. first + len(scalars) - 1, window-table flavour: bucket -> list of points"""
+    half = 1 << (c - 1)
+    buckets = {}
+    for k, s in enumerate(scalars):
+        carry = 0
+        for w in range(nwin):
+            raw = ((s >> (c * w)) & ((1 << c) - 1)) + carry
+            carry = 1 if raw > half else 0
+            mag = (1 << c) - raw if raw > half else raw
+            if mag:
+                p = bn.g1_mul(bases[first + k], 1 << (c * w))
+                buckets.setdefault(mag - 1, []).append(bn.g1_neg(p) if raw > half else p)
+    return buckets
+
+
+def _carry_point(links, b):
+    """carry_point() of msm.cu: the latest earlier piece that holds bucket b decides (it contains the older ones)"""
+    for link in reversed(links):
+        if b in link:
+            return link[b]
+    return INF
+
+
+def linked_pieces_msm(bases, scalars, cuts, c, rounds=0):
+    nwin = -(-257 // c)
+    half = 1 << (c - 1)
+    links = []                                     # per finished piece: {bucket: folded sum} for its non-empty buckets
+    bounds = [0] + list(cuts) + [len(scalars)]
+    last = None
+    for k in range(len(bounds) - 1):
+        lo, hi = bounds[k], bounds[k + 1]
+        mine = _digit_buckets(bases, scalars[lo:hi], lo, c, nwin)
+        keys = sorted(mine)
+        lists = [mine[b] for b in keys]
+        for _ in range(rounds):                    # the rounds see this piece's entries only
+            lists = affine_round(lists)
+        sums = {}
+        for b, lst in zip(keys, lists):            # the walk: opens the bucket with the carry, then adds its own points
+            acc = _carry_point(links, b)
+            for p in lst:
+                acc = bn.g1_add(acc, p)
+            sums[b] = acc
+        if k + 1 < len(bounds) - 1:
+            links.append(sums)
+        else:
+            last = sums
+    acc = INF                                      # the last piece's reduction: own bucket, else what the earlier ones left
+    for b in range(half):
+        s_b = last[b] if b in last else _carry_point(links, b)
+        acc = bn.g1_add(acc, bn.g1_mul(s_b, b + 1))
+    return acc
+
+
+def test_linked_pieces_merge_without_group_operations():
+    rng = random.Random(23)
+    n, c = 48, 5
+    bases = [bn.g1_mul_gen(rng.randrange(1, bn.R)) for _ in range(n)]
+    uniform = [rng.randrange(0, bn.R) for _ in range(n)]
+    skew = list(uniform)
+    for i in range(0, 12):
+        skew[i] = 0                                # the whole first piece contributes nothing
+    for i in range(30, n):
+        skew[i] = rng.randrange(0, 1 << 10)        # short scalars: most buckets empty in the last piece
+    same = [7] * n                                 # one bucket holds everything, in every piece
+    cancel = [3 if i % 2 == 0 else bn.R - 3 for i in range(n)]
+    for scalars in (uniform, skew, same, cancel):
+        want = bn.g1_msm(bases, scalars)
+        for cuts in ((), (12,), (12, 30), (1, 2), (20, 20)):   # one, two, three pieces; tiny and empty ones
+            for rounds in (0, 2):
+                assert linked_pieces_msm(bases, scalars, cuts, c, rounds) == want, (cuts, rounds, scalars[0])
